@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: uint32 keys/s sorted (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload uniform|zipf|unique16|all_equal|sorted|reversed|pairs] [--log2n L]
+
+N = 1: a step is one LSD sort of 2^28 uniform uint32 keys with 8-bit digits (BASELINE config
+1) through libb200sort.so.  `value` = keys/s with the keys resident in HBM (CUDA events on
+the launching stream); `e2e` = the same sort through the reference-facing host entry point
+sort(in, n, out, SORT_BY_DEVICE, nBits, blockSize) with pinned HOST buffers, H2D + D2H inside
+the timed region.  `roofline` is for the dominant kernel (the digit-pass kernel: 8 bytes per
+key per launch), timed live with CUDA events recorded by the library on the sort's stream.
+`cpu_baseline` times the reference's own sortByHost (oracle/_ref when present, else the C
+port) on a bounded sample on the box's host cores.
+
+N > 1 (torchrun, one rank per GPU): a step is one sharded sort of 2^32 keys -- MSD partition,
+NVLink exchange, local LSD sort (cuda/radixsort_b200/mgpu.py).
+
+--impl reference: the reference's CPU sort only (rank 0), on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "uint32 keys/sec sorted"
+UNIT = "keys/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, "of fallback"
+
+
+# --------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def committed_traffic(kernel: str):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sort(sample_log2: int, nbits: int, reps: int, kind_pref: str = "auto"):
+    """Times the reference's sortByHost (single-threaded by construction, Baseline1.cu:30-55)
+    on 2^sample_log2 uniform keys.  Returns (keys_per_s, kind, seconds_per_sort)."""
+    import oracle as O
+    n = 1 << sample_log2
+    keys = O.generate("uniform", n)
+    use_ref = kind_pref != "port" and O.ref_available("Baseline1")
+    fn = (lambda: O.ref_sort_by_host(keys, nbits)) if use_ref else (lambda: O.sort_keys(keys, nbits))
+    times = []
+    out = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        times.append(time.perf_counter() - t0)
+    assert O.is_sorted(out)
+    best = min(times)
+    return n / best, ("reference" if use_ref else "port"), best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_log2 = args.cpu_sample_log2
+    times = []
+    import oracle as O
+    n = 1 << sample_log2
+    keys = O.generate("uniform", n)
+    use_ref = O.ref_available("Baseline1")
+    fn = (lambda: O.ref_sort_by_host(keys, args.nbits)) if use_ref else (lambda: O.sort_keys(keys, args.nbits))
+    for _ in range(args.warmup):
+        fn()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = fn()
+        times.append(time.perf_counter() - t0)
+    assert O.is_sorted(out)
+    total = sum(times)
+    value = n * args.steps / total
+    sample = (f"2^{sample_log2} uniform uint32 keys per step (bounded sample of the 2^{args.log2n}-key "
+              f"workload), sortByHost nBits={args.nbits}, single thread")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1,
+                         "kind": "reference" if use_ref else "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n_gpus: int) -> dict:
+    if n_gpus == 1:
+        what = "key+value pairs" if args.workload == "pairs" else "keys"
+        dist = "uniform" if args.workload == "pairs" else args.workload
+        return {"workload": f"2^{args.log2n} {dist} uint32 {what}, {args.nbits}-bit digits "
+                            f"({-(-32 // args.nbits)} passes), 1 B200",
+                "n": 1 << args.log2n, "nbits": args.nbits, "distribution": dist,
+                "l2": "inputs larger than L2 (1 GiB of keys vs 126 MB), no flush needed"}
+    total_log2 = args.log2n_multi
+    return {"workload": f"2^{total_log2} uniform uint32 keys sharded over {n_gpus} B200: top-digit "
+                        f"histogram + all-reduce splitters, MSD partition, NVLink all-to-all, local LSD sort",
+            "n": 1 << total_log2, "nbits": args.nbits, "distribution": "uniform",
+            "l2": "inputs larger than L2"}
+
+
+# --------------------------------------------------------------------------------------------
+def run_single(args):
+    import torch
+
+    import cuda.radixsort_b200 as rs
+
+    torch.cuda.set_device(0)
+    rs.load()
+    n = 1 << args.log2n
+    nbits = args.nbits
+    pairs = args.workload == "pairs"
+    dist = "uniform" if pairs else args.workload
+    cdf = None
+    if dist == "zipf":
+        import oracle as O          # generator table only (test infrastructure; not the sort)
+        cdf = O.zipf_cdf()
+    keys = rs.generate(dist, n, zipf_cdf=cdf)
+    out = torch.empty_like(keys)
+    vals = vout = None
+    if pairs:
+        vals = torch.arange(n, dtype=torch.int32, device="cuda")
+        vout = torch.empty_like(vals)
+    ws = rs.Workspace("cuda")
+    ws.get(rs.temp_bytes(n, nbits, pairs))
+
+    def step():
+        if pairs:
+            rs.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=vout, workspace=ws)
+        else:
+            rs.sort_keys(keys, nbits, out=out, workspace=ws)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    rs.profile_enable(True)
+    rs.profile_read()
+    launches0 = rs.launch_count()
+    sampler = ClockSampler(0).start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = rs.launch_count() - launches0
+    total_ms = start.elapsed_time(stop)
+    prof = rs.profile_read()
+    rs.profile_enable(False)
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    # correctness of what was just timed: sortedness + multiset fingerprint on the device
+    bad, s1, h1, x1 = rs.verify(out)
+    _, s0, h0, x0 = rs.verify(keys)
+    assert bad == 0 and (s1, h1, x1) == (s0, h0, x0), "timed output is not a sorted permutation of the input"
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    pass_ms = [ms for tag, ms in prof if tag >= 1]
+    hist_ms = [ms for tag, ms in prof if tag == 0]
+    bytes_per_key = 16 if pairs else 8
+    pass_avg = sum(pass_ms) / max(1, len(pass_ms))
+    achieved = bytes_per_key * n / (pass_avg * 1e-3) / 1e9 if pass_ms else None
+    kernel_name = "onesweep_pass_kernel"
+    roofline = {
+        "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None,
+        "traffic": committed_traffic(kernel_name),
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": bytes_per_key * n,
+        "avg_launch_ms": pass_avg, "launches_timed": len(pass_ms),
+        "hist_kernel_avg_ms": (sum(hist_ms) / len(hist_ms)) if hist_ms else None,
+        "kernel_share_of_step": (sum(pass_ms) / total_ms) if pass_ms else None,
+        "whole_sort": {"algorithmic_bytes": rs.algorithmic_bytes(n, nbits, pairs),
+                       "achieved": rs.algorithmic_bytes(n, nbits, pairs) / (ms_per_step * 1e-3) / 1e9,
+                       "frac": rs.algorithmic_bytes(n, nbits, pairs) / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- e2e: host buffers through the reference-facing entry point -------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_out = torch.empty(n, dtype=torch.int32).pin_memory()
+        h_in.copy_(keys)
+        torch.cuda.synchronize()
+        a_in, a_out = h_in.numpy().view(np.uint32), h_out.numpy().view(np.uint32)
+        if pairs:
+            hv_in = torch.arange(n, dtype=torch.int32).pin_memory()
+            hv_out = torch.empty(n, dtype=torch.int32).pin_memory()
+            b_in, b_out = hv_in.numpy().view(np.uint32), hv_out.numpy().view(np.uint32)
+            call = lambda: rs.sort_pairs_by_device(a_in, b_in, n, a_out, b_out, nbits, 512)  # noqa: E731
+        else:
+            call = lambda: rs.sort(a_in, n, a_out, rs.SORT_BY_DEVICE, nbits, 512)            # noqa: E731
+        for _ in range(max(1, min(args.warmup, 2))):
+            call()
+        e2e_steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            call()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        assert a_out[0] <= a_out[n // 2] <= a_out[-1]
+        per = 8 * n if pairs else 4 * n
+        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": per, "d2h_bytes_per_step": per,
+               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "how": "blocking host-pointer call sort(in,n,out,SORT_BY_DEVICE,nBits,512) on pinned "
+                      "host buffers; wall clock around the calls (H2D + sort + D2H inside)"}
+        del h_in, h_out
+
+    # ---- CPU baseline (reported, not the target) ---------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        v, kind, secs = cpu_reference_sort(args.cpu_sample_log2, nbits, args.cpu_reps)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"2^{args.cpu_sample_log2} uniform uint32 keys (bounded sample of the 2^{args.log2n}-key "
+                         f"workload), best of {args.cpu_reps}, sortByHost nBits={nbits}, {secs:.2f} s per sort; "
+                         f"host has {os.cpu_count()} logical cores, the reference CPU sort is single-threaded"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "variant": rs.get_param("variant"), "tile_keys": rs.tile_keys(pairs),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_multi(args):
+    import torch
+    import torch.distributed as dist
+
+    import cuda.radixsort_b200 as rs
+    from cuda.radixsort_b200 import mgpu
+
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rs.load()
+    total = 1 << args.log2n_multi
+    per = total // world
+    keys = rs.generate("uniform", per, first=rank * per, total=total)
+    sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * 1.02) + (1 << 20),
+                                nbits=args.nbits, fused=not args.no_fused)
+    result = None
+    for _ in range(args.warmup):
+        result = sorter.sort(keys)
+    torch.cuda.synchronize(); dist.barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    launches0 = rs.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier(); torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        result = sorter.sort(keys)
+    stop.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([rs.launch_count() - launches0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(launches)
+    phases = sorter.phase_report()          # per-phase ms, max over ranks
+    ok = mgpu.verify_sharded(result, keys, dist.group.WORLD)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        ms_per_step = float(ms.item()) / args.steps
+        line = {
+            "metric": METRIC, "value": total / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(args, world),
+            "phases_ms": phases, "verified": bool(ok), "gpu_launches": int(launches.item()),
+            "clocks": clocks, "roofline": None, "cpu_baseline": None, "e2e": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uniform",
+                    choices=["uniform", "zipf", "unique16", "all_equal", "sorted", "reversed", "pairs"])
+    ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--log2n-multi", type=int, default=32)
+    ap.add_argument("--nbits", type=int, default=8)
+    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--cpu-sample-log2", type=int, default=26)
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.variant is not None:
+        import cuda.radixsort_b200 as rs
+        rs.set_param("variant", args.variant)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        if world == 1:
+            print(json.dumps({"error": "--gpus N > 1 must be launched with torch.distributed.run"}))
+            return 2
+        return run_multi(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

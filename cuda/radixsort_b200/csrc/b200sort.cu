@@ -1,0 +1,632 @@
+// b200sort.cu -- host driver and C ABI of libb200sort.so (see include/b200sort.h).
+//
+// One sort =   memset(header)  ->  K1 hist_kernel (all digit histograms + bases, clears the
+// look-back descriptors)  ->  one onesweep_pass_kernel launch per digit pass (per <2^30-key
+// portion), ping-ponging between the output and one alternate buffer in temp storage.
+// Host side of the reference's sortByDevice (SourceCode/Parallel7.cu:530-639) without its
+// 88 launches, 88 device synchronisations and 4 host round trips per sort.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200sort.h"
+#include "launch.h"
+#include "util_kernels.cuh"
+
+namespace b200sort {
+namespace {
+
+thread_local std::string g_last_error = "";
+std::atomic<uint64_t> g_launches{0};
+
+struct Params {
+    int variant = 0;
+    int portion_tiles = 0;  // 0 = as many as fit the 30-bit descriptor value
+    int hist_ctas_per_sm = 3;
+} g_params;
+
+int g_num_sms = 0;
+int g_device_checked = -1000;
+
+int fail(int code, const char *what) {
+    g_last_error = std::string(what) + ": " + b200sort_error_string(code);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);        \
+    } while (0)
+
+int check_device() {
+    if (g_device_checked != -1000) return g_device_checked;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaGetDevice: ") + cudaGetErrorString(e);
+        return B200SORT_ENODEVICE;  // not cached: a later call may find a device
+    }
+    int major = 0, minor = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10) {
+        g_last_error = "libb200sort is built for sm_100a only; device is sm_" + std::to_string(major) +
+                       std::to_string(minor);
+        return B200SORT_ENODEVICE;
+    }
+    g_num_sms = sms;
+    g_device_checked = 0;
+    return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- digit-pass list ----------------------------------------------------------------------
+// nBits 1..8: one kernel pass per reference digit (the last digit is narrower when
+// 32 % nBits != 0, exactly like the loop at SourceCode/Baseline1.cu:30).
+// nBits 9..16: each reference digit is split into a low sub-digit of ceil(nBits/2) bits and a
+// high sub-digit of the remaining bits, both stable -> same order as one wide pass.
+bool build_pass_list(int nbits, PassList &pl) {
+    if (nbits < 1 || nbits > 16) return false;
+    const int lo = nbits <= kMaxRadixBits ? nbits : (nbits + 1) / 2;
+    pl.width = lo;
+    pl.count = 0;
+    for (int s = 0; s < 32; s += nbits) {
+        const int w = std::min(nbits, 32 - s);
+        pl.shift[pl.count] = (uint8_t)s;
+        pl.bits[pl.count] = (uint8_t)std::min(w, lo);
+        ++pl.count;
+        if (w > lo) {
+            pl.shift[pl.count] = (uint8_t)(s + lo);
+            pl.bits[pl.count] = (uint8_t)(w - lo);
+            ++pl.count;
+        }
+    }
+    return true;
+}
+
+// ---- temp storage layout ---------------------------------------------------------------------
+struct Layout {
+    uint64_t n;
+    int passes, bins;
+    int tile;                // keys per tile of the selected digit-pass kernel
+    uint64_t total_tiles;
+    uint64_t portion_tiles;  // tiles per launch
+    uint64_t portions;
+    // zeroed header: tickets[passes * portions] | done | zeros[bins] | ghist[passes * bins]
+    size_t off_tickets, off_done, off_zeros, off_ghist, header_bytes;
+    size_t off_bin_base;  // [passes][2][bins]
+    size_t off_desc;      // [total_tiles][bins]
+    size_t desc_bytes;
+    size_t off_alt_keys, off_alt_vals;
+    size_t total;
+};
+
+Layout make_layout(uint64_t n, int passes, int width, bool pairs, bool need_alt, int tile,
+                   int portion_tiles_param) {
+    Layout L{};
+    L.n = n;
+    L.passes = passes;
+    L.bins = 1 << width;
+    L.tile = tile;
+    L.total_tiles = (n + tile - 1) / tile;
+    uint64_t cap = ((1ull << 30) - 1) / (uint64_t)tile;
+    if (portion_tiles_param > 0) cap = std::min<uint64_t>(cap, (uint64_t)portion_tiles_param);
+    L.portion_tiles = std::max<uint64_t>(1, std::min<uint64_t>(cap, std::max<uint64_t>(L.total_tiles, 1)));
+    L.portions = std::max<uint64_t>(1, (L.total_tiles + L.portion_tiles - 1) / L.portion_tiles);
+    size_t off = 0;
+    L.off_tickets = off;  off += (size_t)passes * L.portions * 4;
+    off = align_up(off, 16);
+    L.off_done = off;     off += 16;
+    L.off_zeros = off;    off += (size_t)L.bins * 4;
+    L.off_ghist = off;    off += (size_t)passes * L.bins * 4;
+    L.header_bytes = align_up(off, 256);
+    off = L.header_bytes;
+    L.off_bin_base = off; off += (size_t)passes * 2 * L.bins * 4;
+    off = align_up(off, 256);
+    L.off_desc = off;
+    L.desc_bytes = align_up((size_t)L.total_tiles * L.bins * 4, 256);
+    off += L.desc_bytes;
+    L.off_alt_keys = off;
+    if (need_alt) off += align_up((size_t)n * 4, 256);
+    L.off_alt_vals = off;
+    if (need_alt && pairs) off += align_up((size_t)n * 4, 256);
+    L.total = off;
+    return L;
+}
+
+int effective_variant(int width) {
+    return variant_available(width, g_params.variant) ? g_params.variant : 0;
+}
+
+// Upper bound of the temp storage a sort / digit pass can need, independent of the tuning
+// parameters in effect (descriptors sized for the smallest tile, one ticket per pass and
+// per minimal portion).
+size_t temp_upper_bound(uint64_t n, int nbits, bool pairs) {
+    PassList pl;
+    if (!build_pass_list(nbits, pl)) return 0;
+    Layout L = make_layout(n, pl.count, pl.width, pairs, true, kMinTileKeys, 0);
+    size_t extra_tickets = 0;
+    if (g_params.portion_tiles > 0) {
+        const uint64_t tiles = (n + kMinTileKeys - 1) / kMinTileKeys;
+        extra_tickets = align_up((size_t)pl.count * ((tiles / g_params.portion_tiles) + 2) * 4, 256);
+    }
+    return L.total + extra_tickets + 4096;
+}
+
+// ---- profiling events --------------------------------------------------------------------------
+// Marks accumulate over sorts until b200sort_profile_read() drains them.  tag -1 opens a
+// sort; tag 0 closes the histogram kernel; tag p+1 closes digit pass p.
+bool g_profile = false;
+std::vector<cudaEvent_t> g_events;
+std::vector<int> g_event_tags;
+int g_events_used = 0;
+constexpr int kMaxProfileMarks = 1 << 16;
+
+cudaError_t profile_mark(cudaStream_t s, int tag) {
+    if (!g_profile || g_events_used >= kMaxProfileMarks) return cudaSuccess;
+    if (g_events_used == (int)g_events.size()) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) return e;
+        g_events.push_back(ev);
+        g_event_tags.push_back(0);
+    }
+    g_event_tags[g_events_used] = tag;
+    return cudaEventRecord(g_events[g_events_used++], s);
+}
+
+// ---- kernel dispatch by width --------------------------------------------------------------------
+cudaError_t launch_hist(int width, bool uniform, const HistArgs &a, int grid, cudaStream_t s) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (width) {
+    case 1: return launch_hist_w1(uniform, a, grid, s);
+    case 2: return launch_hist_w2(uniform, a, grid, s);
+    case 3: return launch_hist_w3(uniform, a, grid, s);
+    case 4: return launch_hist_w4(uniform, a, grid, s);
+    case 5: return launch_hist_w5(uniform, a, grid, s);
+    case 6: return launch_hist_w6(uniform, a, grid, s);
+    case 7: return launch_hist_w7(uniform, a, grid, s);
+    case 8: return launch_hist_w8(uniform, a, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_pass(int width, int variant, bool pairs, bool dst, const PassArgs &a, cudaStream_t s) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (width) {
+    case 1: return launch_pass_w1(variant, pairs, dst, a, s);
+    case 2: return launch_pass_w2(variant, pairs, dst, a, s);
+    case 3: return launch_pass_w3(variant, pairs, dst, a, s);
+    case 4: return launch_pass_w4(variant, pairs, dst, a, s);
+    case 5: return launch_pass_w5(variant, pairs, dst, a, s);
+    case 6: return launch_pass_w6(variant, pairs, dst, a, s);
+    case 7: return launch_pass_w7(variant, pairs, dst, a, s);
+    case 8: return launch_pass_w8(variant, pairs, dst, a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+int hist_grid(uint64_t n) {
+    const uint64_t per_cta = (uint64_t)kHistThreads * kHistUnroll * 4;
+    const uint64_t want = std::max<uint64_t>(1, (n + per_cta - 1) / per_cta);
+    return (int)std::min<uint64_t>(want, (uint64_t)g_num_sms * g_params.hist_ctas_per_sm);
+}
+
+uint32_t initial_agg_flags(const PassList &pl) {
+    uint32_t f = 0;
+    for (int p = 0; p < pl.count; ++p)
+        if (pl.bits[p] <= 5) f |= 1u << p;
+    return f;
+}
+
+bool ranges_overlap(const void *a, const void *b, uint64_t bytes) {
+    const uintptr_t x = (uintptr_t)a, y = (uintptr_t)b;
+    return x < y + bytes && y < x + bytes;
+}
+
+// ---- the sort ------------------------------------------------------------------------------------
+int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kout, uint32_t *vout,
+             void *temp, size_t temp_bytes, int nbits, cudaStream_t stream) {
+    const bool pairs = (vin != nullptr) || (vout != nullptr);
+    PassList pl;
+    if (!build_pass_list(nbits, pl)) return fail(B200SORT_EINVAL, "nBits must be in 1..16");
+    if (n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    if (n == 0) return B200SORT_OK;
+    if (!kin || !kout || (pairs && (!vin || !vout))) return fail(B200SORT_EINVAL, "null buffer");
+    if (ranges_overlap(kin, kout, n * 4) || (pairs && ranges_overlap(vin, vout, n * 4)))
+        return fail(B200SORT_EALIAS, "output overlaps input");
+    int rc = check_device();
+    if (rc) return rc;
+
+    const int variant = effective_variant(pl.width);
+    const int tile = tile_keys(variant, pairs);
+    const Layout L = make_layout(n, pl.count, pl.width, pairs, true, tile, g_params.portion_tiles);
+    if (!temp || ((uintptr_t)temp & 255u)) return fail(B200SORT_ETEMP, "temp storage must be 256-byte aligned");
+    if (temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage too small");
+
+    char *base = static_cast<char *>(temp);
+    uint32_t *tickets = reinterpret_cast<uint32_t *>(base + L.off_tickets);
+    uint32_t *done = reinterpret_cast<uint32_t *>(base + L.off_done);
+    uint32_t *ghist = reinterpret_cast<uint32_t *>(base + L.off_ghist);
+    uint32_t *bin_base = reinterpret_cast<uint32_t *>(base + L.off_bin_base);
+    uint32_t *desc = reinterpret_cast<uint32_t *>(base + L.off_desc);
+    uint32_t *alt_keys = reinterpret_cast<uint32_t *>(base + L.off_alt_keys);
+    uint32_t *alt_vals = reinterpret_cast<uint32_t *>(base + L.off_alt_vals);
+
+    CU(cudaMemsetAsync(base, 0, L.header_bytes, stream));
+    CU(profile_mark(stream, -1));
+
+    HistArgs h{};
+    h.keys = kin;
+    h.n = n;
+    h.ghist = ghist;
+    h.bin_base = bin_base;
+    h.done = done;
+    h.zero_ptr = reinterpret_cast<uint4 *>(desc);
+    h.zero_vecs = L.desc_bytes / 16;
+    h.agg_init = initial_agg_flags(pl);
+    h.passes = pl;
+    CU(launch_hist(pl.width, nbits <= kMaxRadixBits, h, hist_grid(n), stream));
+    CU(profile_mark(stream, 0));
+
+    const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
+    for (int p = 0; p < pl.count; ++p) {
+        const bool to_out = ((pl.count - 1 - p) & 1) == 0;
+        const uint32_t *src_k = (p == 0) ? kin : (to_out ? alt_keys : kout);
+        const uint32_t *src_v = (p == 0) ? vin : (to_out ? alt_vals : vout);
+        uint32_t *dst_k = to_out ? kout : alt_keys;
+        uint32_t *dst_v = to_out ? vout : alt_vals;
+        for (uint64_t q = 0; q < L.portions; ++q) {
+            const uint64_t first = q * portion_keys;
+            const uint64_t count = std::min<uint64_t>(portion_keys, n - first);
+            PassArgs a{};
+            a.keys_in = src_k + first;
+            a.vals_in = pairs ? src_v + first : nullptr;
+            a.keys_out = dst_k;
+            a.vals_out = pairs ? dst_v : nullptr;
+            a.bin_base = bin_base + ((size_t)(2 * p) + (q & 1)) * L.bins;
+            a.carry_out = (q + 1 < L.portions) ? bin_base + ((size_t)(2 * p) + ((q + 1) & 1)) * L.bins : nullptr;
+            a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
+            a.ticket = tickets + (size_t)p * L.portions + q;
+            a.bin_dst = nullptr;
+            a.n = (uint32_t)count;
+            a.num_tiles = (uint32_t)((count + tile - 1) / tile);
+            a.shift = pl.shift[p];
+            a.mask = (1u << pl.bits[p]) - 1u;
+            a.parity = (uint32_t)(p & 1);
+            CU(launch_pass(pl.width, variant, pairs, false, a, stream));
+        }
+        CU(profile_mark(stream, p + 1));
+    }
+    return B200SORT_OK;
+}
+
+// ---- host-pointer wrapper state --------------------------------------------------------------------
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    void *d_buf = nullptr;  // [keys_in | vals_in | keys_out | vals_out | temp]
+    size_t d_bytes = 0;
+} g_host;
+
+int ensure_host_ctx(size_t bytes) {
+    if (!g_host.stream) CU(cudaStreamCreateWithFlags(&g_host.stream, cudaStreamNonBlocking));
+    if (g_host.d_bytes < bytes) {
+        if (g_host.d_buf) CU(cudaFree(g_host.d_buf));
+        g_host.d_buf = nullptr;
+        g_host.d_bytes = 0;
+        cudaError_t e = cudaMalloc(&g_host.d_buf, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200SORT_ENOMEM, "cudaMalloc of device staging buffers");
+        }
+        g_host.d_bytes = bytes;
+    }
+    return 0;
+}
+
+int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t *hk_out,
+              uint32_t *hv_out, int nbits, int block_size, bool pairs) {
+    PassList pl;
+    if (!build_pass_list(nbits, pl)) return fail(B200SORT_EINVAL, "nBits must be in 1..16");
+    if (block_size <= 0) return fail(B200SORT_EINVAL, "blockSize must be positive");
+    if (n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    if (n == 0) return B200SORT_OK;
+    if (!hk_in || !hk_out || (pairs && (!hv_in || !hv_out))) return fail(B200SORT_EINVAL, "null buffer");
+    int rc = check_device();
+    if (rc) return rc;
+
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    const size_t arr = align_up((size_t)n * 4, 256);
+    const size_t temp_bytes = temp_upper_bound(n, nbits, pairs);
+    const size_t arrays = pairs ? 4 : 2;
+    rc = ensure_host_ctx(arrays * arr + temp_bytes);
+    if (rc) return rc;
+    char *b = static_cast<char *>(g_host.d_buf);
+    uint32_t *dk_in = reinterpret_cast<uint32_t *>(b);
+    uint32_t *dk_out = reinterpret_cast<uint32_t *>(b + arr);
+    uint32_t *dv_in = pairs ? reinterpret_cast<uint32_t *>(b + 2 * arr) : nullptr;
+    uint32_t *dv_out = pairs ? reinterpret_cast<uint32_t *>(b + 3 * arr) : nullptr;
+    void *temp = b + arrays * arr;
+    cudaStream_t s = g_host.stream;
+
+    CU(cudaMemcpyAsync(dk_in, hk_in, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if (pairs) CU(cudaMemcpyAsync(dv_in, hv_in, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    rc = run_sort(dk_in, dv_in, n, dk_out, dv_out, temp, temp_bytes, nbits, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(hk_out, dk_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (pairs) CU(cudaMemcpyAsync(hv_out, dv_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return B200SORT_OK;
+}
+
+}  // namespace
+}  // namespace b200sort
+
+using namespace b200sort;
+
+// =====================================================================================================
+extern "C" {
+
+int b200sort_version(void) { return B200SORT_VERSION; }
+
+const char *b200sort_error_string(int code) {
+    switch (code) {
+    case B200SORT_OK: return "ok";
+    case B200SORT_EINVAL: return "invalid argument";
+    case B200SORT_ETOOBIG: return "n exceeds 2^32-1 keys";
+    case B200SORT_ETEMP: return "temp storage too small or misaligned";
+    case B200SORT_EALIAS: return "output aliases input";
+    case B200SORT_ENODEVICE: return "no usable sm_100 device";
+    case B200SORT_ENOMEM: return "out of device memory";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+const char *b200sort_last_error_string(void) { return g_last_error.c_str(); }
+
+uint64_t b200sort_launch_count(void) { return g_launches.load(); }
+
+int b200sort_num_passes(int nBits) {
+    PassList pl;
+    return build_pass_list(nBits, pl) ? pl.count : B200SORT_EINVAL;
+}
+
+uint64_t b200sort_algorithmic_bytes(uint64_t n, int nBits, int pairs) {
+    PassList pl;
+    if (!build_pass_list(nBits, pl)) return 0;
+    const uint64_t P = (uint64_t)pl.count;
+    return 4ull * n * (pairs ? 4 * P + 1 : 2 * P + 1);
+}
+
+int b200sort_tile_keys(int pairs) { return tile_keys(effective_variant(8), pairs != 0); }
+
+size_t b200sort_temp_bytes(uint64_t n, int nBits, int pairs) {
+    return temp_upper_bound(n, nBits, pairs != 0);
+}
+
+int b200sort_set_param(const char *name, int value) {
+    if (!name) return B200SORT_EINVAL;
+    if (!strcmp(name, "variant")) {
+        if (value < 0 || value >= kNumVariants) return B200SORT_EINVAL;
+        g_params.variant = value;
+        return 0;
+    }
+    if (!strcmp(name, "portion_tiles")) {
+        if (value < 0) return B200SORT_EINVAL;
+        g_params.portion_tiles = value;
+        return 0;
+    }
+    if (!strcmp(name, "hist_ctas_per_sm")) {
+        if (value < 1 || value > 4) return B200SORT_EINVAL;
+        g_params.hist_ctas_per_sm = value;
+        return 0;
+    }
+    return B200SORT_EINVAL;
+}
+
+int b200sort_get_param(const char *name) {
+    if (!name) return B200SORT_EINVAL;
+    if (!strcmp(name, "variant")) return g_params.variant;
+    if (!strcmp(name, "portion_tiles")) return g_params.portion_tiles;
+    if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
+    return B200SORT_EINVAL;
+}
+
+int b200sort_keys(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp, size_t temp_bytes,
+                  int nBits, void *stream) {
+    return run_sort(d_in, nullptr, n, d_out, nullptr, d_temp, temp_bytes, nBits, (cudaStream_t)stream);
+}
+
+int b200sort_pairs(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                   uint32_t *d_keys_out, uint32_t *d_vals_out, void *d_temp, size_t temp_bytes,
+                   int nBits, void *stream) {
+    if (n > 0 && (!d_vals_in || !d_vals_out)) return fail(B200SORT_EINVAL, "null value buffer");
+    return run_sort(d_keys_in, d_vals_in, n, d_keys_out, d_vals_out, d_temp, temp_bytes, nBits,
+                    (cudaStream_t)stream);
+}
+
+int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nBits, int blockSize) {
+    return sort_host(h_in, nullptr, n, h_out, nullptr, nBits, blockSize, false);
+}
+
+int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n,
+                        uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits, int blockSize) {
+    return sort_host(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, nBits, blockSize, true);
+}
+
+int b200sort_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    if (g_host.d_buf) cudaFree(g_host.d_buf);
+    g_host.d_buf = nullptr;
+    g_host.d_bytes = 0;
+    if (g_host.stream) cudaStreamDestroy(g_host.stream);
+    g_host.stream = nullptr;
+    for (cudaEvent_t ev : g_events) cudaEventDestroy(ev);
+    g_events.clear();
+    g_event_tags.clear();
+    g_events_used = 0;
+    return 0;
+}
+
+int b200sort_histogram(const uint32_t *d_keys, uint64_t n, int shift, int bits, uint32_t *d_hist,
+                       void *d_temp, size_t temp_bytes, void *stream) {
+    if (bits < 1 || bits > kMaxRadixBits || shift < 0 || shift > 31) return fail(B200SORT_EINVAL, "shift/bits");
+    if (!d_hist || (n > 0 && !d_keys)) return fail(B200SORT_EINVAL, "null buffer");
+    if (n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    int rc = check_device();
+    if (rc) return rc;
+    const int bins = 1 << bits;
+    const size_t need = 256 + (size_t)2 * bins * 4;
+    if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < need) return fail(B200SORT_ETEMP, "temp storage");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_temp, 0, 256, s));
+    CU(cudaMemsetAsync(d_hist, 0, (size_t)bins * 4, s));
+    if (n == 0) return 0;
+    HistArgs h{};
+    h.keys = d_keys;
+    h.n = n;
+    h.ghist = d_hist;
+    h.done = static_cast<uint32_t *>(d_temp);
+    h.bin_base = reinterpret_cast<uint32_t *>(static_cast<char *>(d_temp) + 256);
+    h.zero_ptr = nullptr;
+    h.zero_vecs = 0;
+    h.passes.count = 1;
+    h.passes.width = bits;
+    h.passes.shift[0] = (uint8_t)shift;
+    h.passes.bits[0] = (uint8_t)std::min(bits, 32 - shift);
+    h.agg_init = initial_agg_flags(h.passes);
+    CU(launch_hist(bits, false, h, hist_grid(n), s));
+    return 0;
+}
+
+int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                        uint32_t *d_keys_out, uint32_t *d_vals_out, int shift, int bits,
+                        const uint64_t *d_bin_dst, void *d_temp, size_t temp_bytes, void *stream) {
+    if (bits < 1 || bits > kMaxRadixBits || shift < 0 || shift > 31) return fail(B200SORT_EINVAL, "shift/bits");
+    const bool pairs = d_vals_in != nullptr;
+    const bool dst = d_bin_dst != nullptr;
+    if (n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    if (n == 0) return 0;
+    if (!d_keys_in || (!dst && !d_keys_out) || (pairs && !dst && !d_vals_out))
+        return fail(B200SORT_EINVAL, "null buffer");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const int variant = dst ? 0 : effective_variant(bits);
+    const int tile = tile_keys(variant, pairs);
+    const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);
+    if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage");
+    char *base = static_cast<char *>(d_temp);
+    uint32_t *tickets = reinterpret_cast<uint32_t *>(base + L.off_tickets);
+    uint32_t *bin_base = reinterpret_cast<uint32_t *>(base + L.off_bin_base);
+    uint32_t *desc = reinterpret_cast<uint32_t *>(base + L.off_desc);
+
+    CU(cudaMemsetAsync(base, 0, L.header_bytes, s));
+    if (!dst) {
+        HistArgs h{};
+        h.keys = d_keys_in;
+        h.n = n;
+        h.ghist = reinterpret_cast<uint32_t *>(base + L.off_ghist);
+        h.bin_base = bin_base;
+        h.done = reinterpret_cast<uint32_t *>(base + L.off_done);
+        h.zero_ptr = reinterpret_cast<uint4 *>(desc);
+        h.zero_vecs = L.desc_bytes / 16;
+        h.passes.count = 1;
+        h.passes.width = bits;
+        h.passes.shift[0] = (uint8_t)shift;
+        h.passes.bits[0] = (uint8_t)std::min(bits, 32 - shift);
+        h.agg_init = initial_agg_flags(h.passes);
+        CU(launch_hist(bits, false, h, hist_grid(n), s));
+    } else {
+        // Destinations are per-bin arrays: offsets inside a bin start at zero.
+        CU(cudaMemsetAsync(bin_base, 0, (size_t)2 * L.bins * 4, s));
+        CU(cudaMemsetAsync(desc, 0, L.desc_bytes, s));
+    }
+    const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
+    for (uint64_t q = 0; q < L.portions; ++q) {
+        const uint64_t first = q * portion_keys;
+        const uint64_t count = std::min<uint64_t>(portion_keys, n - first);
+        PassArgs a{};
+        a.keys_in = d_keys_in + first;
+        a.vals_in = pairs ? d_vals_in + first : nullptr;
+        a.keys_out = d_keys_out;
+        a.vals_out = d_vals_out;
+        a.bin_base = bin_base + (q & 1) * L.bins;
+        a.carry_out = (q + 1 < L.portions) ? bin_base + ((q + 1) & 1) * L.bins : nullptr;
+        a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
+        a.ticket = tickets + q;
+        a.bin_dst = d_bin_dst;
+        a.n = (uint32_t)count;
+        a.num_tiles = (uint32_t)((count + tile - 1) / tile);
+        a.shift = (uint32_t)shift;
+        a.mask = (1u << std::min(bits, 32 - shift)) - 1u;
+        a.parity = 0;
+        CU(launch_pass(bits, variant, pairs, dst, a, s));
+    }
+    return 0;
+}
+
+int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind, uint64_t total,
+                      const uint32_t *d_zipf_cdf, void *stream) {
+    if (kind < GEN_UNIFORM || kind > GEN_IOTA) return fail(B200SORT_EINVAL, "generator kind");
+    if (kind == GEN_ZIPF && !d_zipf_cdf) return fail(B200SORT_EINVAL, "zipf needs the cdf table");
+    if (count == 0) return 0;
+    if (!d_out) return fail(B200SORT_EINVAL, "null buffer");
+    int rc = check_device();
+    if (rc) return rc;
+    const int grid = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)g_num_sms * 16);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    generate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_out, first, count, kind, total, d_zipf_cdf);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void *stream) {
+    if (!d_result || (n > 0 && !d_keys)) return fail(B200SORT_EINVAL, "null buffer");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_result, 0, 4 * sizeof(uint64_t), s));
+    if (n == 0) return 0;
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)g_num_sms * 16);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    verify_kernel<<<grid, 256, 0, s>>>(d_keys, n, reinterpret_cast<unsigned long long *>(d_result));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int b200sort_profile_enable(int on) {
+    g_profile = on != 0;
+    g_events_used = 0;
+    return 0;
+}
+
+int b200sort_profile_read(float *ms, int *tag, int capacity) {
+    if (!ms || !tag || capacity < 0) return B200SORT_EINVAL;
+    int out = 0;
+    if (g_events_used >= 2) {
+        CU(cudaEventSynchronize(g_events[g_events_used - 1]));
+        for (int i = 1; i < g_events_used && out < capacity; ++i) {
+            if (g_event_tags[i] < 0) continue;  // a new sort starts here
+            CU(cudaEventElapsedTime(&ms[out], g_events[i - 1], g_events[i]));
+            tag[out] = g_event_tags[i];
+            ++out;
+        }
+    }
+    g_events_used = 0;
+    return out;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// util_kernels.cuh -- device side of the synthetic workloads and the
+// size-independent output checks (sortedness + multiset fingerprint).  Bench/test utilities;
+// they generate the same bytes as oracle/radix_oracle.c:oracle_generate.
+#pragma once
+#include "common.cuh"
+
+namespace b200sort {
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+enum { GEN_UNIFORM = 0, GEN_ZIPF = 1, GEN_UNIQUE16 = 2, GEN_ALL_EQUAL = 3, GEN_SORTED = 4,
+       GEN_REVERSED = 5, GEN_IOTA = 6 };
+
+__global__ void __launch_bounds__(256) generate_kernel(uint32_t *out, uint64_t first, uint64_t count,
+                                                       int kind, uint64_t total,
+                                                       const uint32_t *__restrict__ cdf) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count;
+         j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = first + j;
+        uint32_t k = 0;
+        switch (kind) {
+        case GEN_UNIFORM: k = (uint32_t)(splitmix64(0x5EED0001ULL + i) >> 32); break;
+        case GEN_ZIPF: {
+            const uint32_t u = (uint32_t)(splitmix64(0x5EED0004ULL + i) >> 32);
+            int lo = 0, hi = 65535;  // first r with cdf[r] >= u
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cdf[mid] >= u) hi = mid; else lo = mid + 1;
+            }
+            k = (uint32_t)(splitmix64((uint64_t)lo) >> 32);
+            break;
+        }
+        case GEN_UNIQUE16: k = (uint32_t)(splitmix64(splitmix64(0x5EED0005ULL + i) & 15ULL) >> 32); break;
+        case GEN_ALL_EQUAL: k = 0xDEADBEEFu; break;
+        case GEN_SORTED:
+        case GEN_REVERSED:
+            k = (uint32_t)((i << 32) / (total ? total : 1ULL));  // i < 2^32
+            if (kind == GEN_REVERSED) k = ~k;
+            break;
+        case GEN_IOTA: k = (uint32_t)i; break;
+        }
+        out[j] = k;
+    }
+}
+
+// result[0] += #{i >= 1 : keys[i-1] > keys[i]}, result[1] += sum key, result[2] += sum sm64(key),
+// result[3] ^= xor sm64(key).
+__global__ void __launch_bounds__(256) verify_kernel(const uint32_t *__restrict__ keys, uint64_t n,
+                                                     unsigned long long *result) {
+    unsigned long long bad = 0, s = 0, h = 0, x = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        if (i > 0 && keys[i - 1] > k) ++bad;
+        const uint64_t m = splitmix64((uint64_t)k);
+        s += k;
+        h += m;
+        x ^= m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        h += __shfl_xor_sync(0xffffffffu, h, o);
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&result[0], bad);
+        atomicAdd(&result[1], s);
+        atomicAdd(&result[2], h);
+        atomicXor(&result[3], x);
+    }
+}
+
+}  // namespace b200sort

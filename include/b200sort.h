@@ -1,0 +1,159 @@
+/*
+ * b200sort.h -- C ABI of libb200sort.so, a B200 (sm_100a) LSD radix sort for uint32 keys and
+ * stable uint32 key/value pairs.
+ *
+ * This is the drop-in boundary for the device sort path of truongchauhien/CUDA.RadixSort.
+ * The reference has no FFI layer: its boundary is a set of free C++ functions in one
+ * translation unit.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B200SORT_E* code / positive
+ *     cudaError_t; the library never prints and never calls exit() (the reference's CHECK
+ *     macro, SourceCode/common/common.h:6-16, prints and exits -- the C++ shim
+ *     include/radix_sort_compat.hpp reproduces that on top of these return codes);
+ *   - there is NO CPU path: every sort runs the hand-written sm_100a kernels or fails;
+ *   - n is 64-bit in the ABI (the reference's `int n` caps it at 2^31-1); one call sorts
+ *     at most 2^32-1 keys on one GPU;
+ *   - nBits is the reference's digit width (SourceCode/Parallel7.cu:644): 1..16.  Widths
+ *     1..8 run one kernel pass per digit; widths 9..16 run each digit as two stable
+ *     sub-digit passes (the sorted output of an LSD sort does not depend on the width);
+ *   - blockSize is accepted for signature compatibility (SourceCode/Parallel7.cu:645) and
+ *     validated (> 0) but advisory: the kernels fix their own tile geometry and the output
+ *     never depends on it.
+ */
+#ifndef B200SORT_H_
+#define B200SORT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SORT_VERSION 100
+
+enum {
+    B200SORT_OK = 0,
+    B200SORT_EINVAL = -1,     /* bad argument (null pointer, nBits outside 1..16, blockSize <= 0) */
+    B200SORT_ETOOBIG = -2,    /* n > 2^32-1 */
+    B200SORT_ETEMP = -3,      /* temp buffer too small or misaligned */
+    B200SORT_EALIAS = -4,     /* d_out aliases d_in */
+    B200SORT_ENODEVICE = -5,  /* no sm_100 device / CUDA runtime unusable */
+    B200SORT_ENOMEM = -6      /* host-pointer wrapper could not allocate */
+};
+
+/* ---------------------------------------------------------------------------------------
+ * Host-pointer entry points: same semantics as the reference's
+ *   void sortByDevice(const uint32_t *h_input, int n, uint32_t *h_output, int numBits,
+ *                     int blockSize)                       -- SourceCode/Parallel7.cu:530
+ * (called from sort(), SourceCode/Parallel7.cu:641-662).  The caller owns the host arrays
+ * (pageable or pinned); h_in is not modified; h_out is fully overwritten; h_out == h_in is
+ * allowed.  Blocking.  Device buffers are cached by the library between calls and released
+ * by b200sort_shutdown().  One call at a time per process (internally serialised).
+ */
+int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nBits,
+                       int blockSize);
+
+/* Key/value extension named by the north star (the reference has no pairs path).  Stable:
+ * equal keys keep their input order. */
+int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n,
+                        uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits, int blockSize);
+
+/* Frees the cached device/pinned buffers of the host-pointer entry points. */
+int b200sort_shutdown(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident entry points: the per-digit loop of sortByDevice
+ * (SourceCode/Parallel7.cu:561-622: sortLocallyDataBlocks + histogram + transpose/scan/
+ * transpose + scatter) without its cudaMalloc/H2D/D2H shell.  Asynchronous on `stream`
+ * (a cudaStream_t; NULL = default stream).  The caller owns every buffer.  d_in is not
+ * modified; d_out must not overlap d_in.  d_temp must be 256-byte aligned and at least
+ * b200sort_temp_bytes() long.  n == 0 is a no-op (undefined in the reference,
+ * SourceCode/Parallel7.cu:157).
+ */
+size_t b200sort_temp_bytes(uint64_t n, int nBits, int pairs);
+
+int b200sort_keys(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp,
+                  size_t temp_bytes, int nBits, void *stream);
+
+int b200sort_pairs(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                   uint32_t *d_keys_out, uint32_t *d_vals_out, void *d_temp,
+                   size_t temp_bytes, int nBits, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Building blocks, exported for the multi-GPU driver (histogram -> splitters -> partition ->
+ * exchange -> local sort) and as the public form of the reference's stage wrappers.
+ */
+
+/* Digit histogram of (key >> shift) & (2^bits - 1), bits in 1..8; d_hist[2^bits] uint32 is
+ * overwritten.  Replaces histogram() + histogramKernel, SourceCode/Parallel7.cu:318-359,
+ * reduced over tiles (the tile x bin table itself never exists in this design). */
+int b200sort_histogram(const uint32_t *d_keys, uint64_t n, int shift, int bits,
+                       uint32_t *d_hist, void *d_temp, size_t temp_bytes, void *stream);
+
+/* One stable counting-sort pass on the digit (key >> shift) & (2^bits - 1), bits in 1..8:
+ * out = keys ordered by that digit, ties in input order.  This is one iteration of the
+ * reference's digit loop (SourceCode/Parallel7.cu:561-622) and, with shift = 32 - bits, the
+ * MSD range partition of the multi-GPU sort.  d_vals_in/d_vals_out may both be NULL.
+ * If d_bin_dst is non-NULL it holds 2^bits device addresses (uint64): the keys of bin d
+ * are written to ((uint32_t*)d_bin_dst[d])[0 .. count_d) instead of d_keys_out (and values
+ * to d_bin_dst[2^bits + d]) -- the addresses may be peer (NVLink) memory, which fuses the
+ * partition with the exchange.  Temp size: b200sort_temp_bytes(n, bits, pairs). */
+int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                        uint32_t *d_keys_out, uint32_t *d_vals_out, int shift, int bits,
+                        const uint64_t *d_bin_dst, void *d_temp, size_t temp_bytes,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement and test utilities (device side of SURVEY.md section 8d's workloads).
+ */
+enum {
+    B200SORT_GEN_UNIFORM = 0, B200SORT_GEN_ZIPF = 1, B200SORT_GEN_UNIQUE16 = 2,
+    B200SORT_GEN_ALL_EQUAL = 3, B200SORT_GEN_SORTED = 4, B200SORT_GEN_REVERSED = 5,
+    B200SORT_GEN_IOTA = 6
+};
+
+/* d_out[j] = key(first + j), j < count; `total` scales the sorted/reversed ramps;
+ * d_zipf_cdf (65536 uint32) is only read for B200SORT_GEN_ZIPF. */
+int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind,
+                      uint64_t total, const uint32_t *d_zipf_cdf, void *stream);
+
+/* d_result[0] = number of i with keys[i-1] > keys[i]; d_result[1..3] = order-independent
+ * multiset fingerprint (sum key, sum sm64(key), xor sm64(key)).  d_result: 4 x uint64,
+ * overwritten. */
+int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void *stream);
+
+/* Per-kernel device timing: while enabled, every sort records CUDA events on its own stream
+ * around each kernel.  b200sort_profile_read() synchronises on the last recorded event,
+ * drains the records of all sorts since the previous read and returns how many it wrote:
+ * ms[i] is a kernel duration, tag[i] says which kernel (0 = histogram kernel, p+1 = digit
+ * pass p, all launches of that pass together). */
+int b200sort_profile_enable(int on);
+int b200sort_profile_read(float *ms, int *tag, int capacity);
+
+/* Number of kernels this library has launched since load (the bench's gpu_launches). */
+uint64_t b200sort_launch_count(void);
+
+/* Tuning hooks (bench/test use): "variant" selects the digit-pass kernel geometry,
+ * "portion_tiles" caps tiles per launch (0 = default; tests use it to exercise the
+ * multi-launch path at small n), "hist_ctas_per_sm".  Returns B200SORT_EINVAL for an
+ * unknown name or value. */
+int b200sort_set_param(const char *name, int value);
+int b200sort_get_param(const char *name);
+
+/* Geometry of the selected digit-pass kernel (keys per tile), algorithmic byte count
+ * 4n(2P+1) / 4n(4P+1) of SURVEY.md section 8d, and number of digit passes actually run. */
+int b200sort_tile_keys(int pairs);
+uint64_t b200sort_algorithmic_bytes(uint64_t n, int nBits, int pairs);
+int b200sort_num_passes(int nBits);
+
+int b200sort_version(void);
+const char *b200sort_error_string(int code);
+const char *b200sort_last_error_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SORT_H_ */
