@@ -26,8 +26,12 @@ std::atomic<uint64_t> g_launches{0};
 struct Params {
     int variant = 0;
     int portion_tiles = 0;  // 0 = as many as fit the 30-bit descriptor value
-    int hist_ctas_per_sm = 3;
+    int hist_ctas_per_sm = 2;
 } g_params;
+
+// RANK_ATOMIC variants are only used after the on-device self test has passed.
+// -1 = not run yet, 0 = failed (fall back to the table-rank twin), 1 = passed.
+int g_atomic_rank_ok = -1;
 
 int g_num_sms = 0;
 int g_device_checked = -1000;
@@ -144,8 +148,31 @@ Layout make_layout(uint64_t n, int passes, int width, bool pairs, bool need_alt,
     return L;
 }
 
+int check_device();
+
+int run_selftest() {
+    if (g_atomic_rank_ok >= 0) return g_atomic_rank_ok;
+    if (check_device() != 0) return 0;  // not cached: no device yet
+    uint32_t *d_counter = nullptr;
+    uint32_t h = 1;
+    if (cudaMalloc(&d_counter, sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    bool ok = cudaMemset(d_counter, 0, sizeof(uint32_t)) == cudaSuccess &&
+              run_atomic_order_selftest(d_counter, g_num_sms * 2, 4096, nullptr) == cudaSuccess &&
+              cudaMemcpy(&h, d_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaFree(d_counter);
+    g_atomic_rank_ok = (ok && h == 0) ? 1 : 0;
+    return g_atomic_rank_ok;
+}
+
 int effective_variant(int width) {
-    return variant_available(width, g_params.variant) ? g_params.variant : 0;
+    int v = variant_available(width, g_params.variant) ? g_params.variant : 0;
+    if (variant_mode(v) == 1 && !run_selftest()) {
+        // same geometry, table rank: variants are laid out as (table, atomic) twins where possible
+        v = (v >= 1 && variant_mode(v - 1) == 0 && kVariants[v - 1].threads == kVariants[v].threads &&
+             kVariants[v - 1].items_keys == kVariants[v].items_keys) ? v - 1 : 0;
+    }
+    return v;
 }
 
 // Upper bound of the temp storage a sort / digit pass can need, independent of the tuning
@@ -215,17 +242,13 @@ cudaError_t launch_pass(int width, int variant, bool pairs, bool dst, const Pass
     return cudaErrorInvalidValue;
 }
 
-int hist_grid(uint64_t n) {
+int hist_grid(uint64_t n, int passes, int width) {
     const uint64_t per_cta = (uint64_t)kHistThreads * kHistUnroll * 4;
     const uint64_t want = std::max<uint64_t>(1, (n + per_cta - 1) / per_cta);
-    return (int)std::min<uint64_t>(want, (uint64_t)g_num_sms * g_params.hist_ctas_per_sm);
-}
-
-uint32_t initial_agg_flags(const PassList &pl) {
-    uint32_t f = 0;
-    for (int p = 0; p < pl.count; ++p)
-        if (pl.bits[p] <= 5) f |= 1u << p;
-    return f;
+    const size_t smem = hist_smem_bytes(passes, width) + 1024;
+    int ctas = (int)std::min<size_t>((size_t)g_params.hist_ctas_per_sm, (227u * 1024u) / smem);
+    ctas = std::max(1, std::min(ctas, 2048 / kHistThreads));
+    return (int)std::min<uint64_t>(want, (uint64_t)g_num_sms * ctas);
 }
 
 bool ranges_overlap(const void *a, const void *b, uint64_t bytes) {
@@ -273,9 +296,8 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
     h.done = done;
     h.zero_ptr = reinterpret_cast<uint4 *>(desc);
     h.zero_vecs = L.desc_bytes / 16;
-    h.agg_init = initial_agg_flags(pl);
     h.passes = pl;
-    CU(launch_hist(pl.width, nbits <= kMaxRadixBits, h, hist_grid(n), stream));
+    CU(launch_hist(pl.width, nbits <= kMaxRadixBits, h, hist_grid(n, pl.count, pl.width), stream));
     CU(profile_mark(stream, 0));
 
     const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
@@ -440,6 +462,9 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "variant")) return g_params.variant;
     if (!strcmp(name, "portion_tiles")) return g_params.portion_tiles;
     if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
+    if (!strcmp(name, "num_variants")) return kNumVariants;
+    if (!strcmp(name, "effective_variant")) return check_device() ? g_params.variant : effective_variant(8);
+    if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
     return B200SORT_EINVAL;
 }
 
@@ -505,8 +530,7 @@ int b200sort_histogram(const uint32_t *d_keys, uint64_t n, int shift, int bits, 
     h.passes.width = bits;
     h.passes.shift[0] = (uint8_t)shift;
     h.passes.bits[0] = (uint8_t)std::min(bits, 32 - shift);
-    h.agg_init = initial_agg_flags(h.passes);
-    CU(launch_hist(bits, false, h, hist_grid(n), s));
+    CU(launch_hist(bits, false, h, hist_grid(n, 1, bits), s));
     return 0;
 }
 
@@ -524,7 +548,8 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
 
-    const int variant = dst ? 0 : effective_variant(bits);
+    int variant = effective_variant(bits);
+    if (dst && variant > 1) variant = 0;
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);
     if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage");
@@ -547,8 +572,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
         h.passes.width = bits;
         h.passes.shift[0] = (uint8_t)shift;
         h.passes.bits[0] = (uint8_t)std::min(bits, 32 - shift);
-        h.agg_init = initial_agg_flags(h.passes);
-        CU(launch_hist(bits, false, h, hist_grid(n), s));
+        CU(launch_hist(bits, false, h, hist_grid(n, 1, bits), s));
     } else {
         // Destinations are per-bin arrays: offsets inside a bin start at zero.
         CU(cudaMemsetAsync(bin_base, 0, (size_t)2 * L.bins * 4, s));

@@ -10,7 +10,7 @@ namespace b200sort {
 
 constexpr int kMaxPasses = 32;       // nBits = 1 -> 32 digit passes
 constexpr int kMaxRadixBits = 8;     // widest digit one kernel pass handles
-constexpr int kHistThreads = 512;
+constexpr int kHistThreads = 1024;
 constexpr int kHistUnroll = 4;       // uint4 loads in flight per thread
 constexpr uint32_t kDescValueMask = 0x3FFFFFFFu;
 constexpr uint32_t kDescFlagMask = 0xC0000000u;
@@ -33,7 +33,6 @@ struct HistArgs {
     uint32_t *done;      // zeroed CTA counter
     uint4 *zero_ptr;     // side job: region to clear (look-back descriptors)
     uint64_t zero_vecs;
-    uint32_t agg_init;   // passes that start in warp-aggregated mode
     PassList passes;
 };
 

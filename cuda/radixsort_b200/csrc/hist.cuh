@@ -5,11 +5,14 @@
 // launches once per digit pass with one global atomic per tile x bin and a memset before it,
 // and the part of scan() (:485-528) that produced the per-bin bases.
 //
-// Counting is done in shared memory.  Each pass starts in "plain" mode (one shared atomic per
-// key) and switches, per pass and per CTA, to warp-aggregated mode (match.any + one atomic per
-// distinct digit in the warp) once a bin of that pass holds more than 1/8 of the keys seen so
-// far -- the point where same-address conflicts cost more than the match.  Narrow digits
-// (<= 5 bits) start aggregated.
+// Shared-memory layout: s_hist[pass][bin][lane] -- every lane of a warp owns its own column,
+// so the 32 shared atomics of one warp instruction always hit 32 different banks, whatever
+// the key distribution (uniform, all-equal, 16 values, Zipf: same speed).  Measured on B200
+// (profiles/r01_probe_b200.json): shared atomics on random bins of ONE 256-entry table run
+// at ~3.2 cycles per warp instruction (bank conflicts), conflict-free ones at ~1.4; with 4
+// digits per key the first layout is atomics-bound at ~0.37 ms for 2^28 keys, the lane-private
+// one sits at the DRAM time (~0.17 ms).  match.any aggregation is not used: MATCH.ANY issues
+// at ~1 warp instruction per 61 cycles per SM on this part.
 #pragma once
 #include "common.cuh"
 
@@ -18,21 +21,21 @@ namespace b200sort {
 // W: log2 of bins per pass.  P_CT > 0: uniform pass list (pass p = bits [p*W, p*W+W)) known at
 // compile time; P_CT == 0: runtime list from args.passes.
 template <int W, int P_CT>
-__global__ void __launch_bounds__(kHistThreads) hist_kernel(const HistArgs a) {
+__global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a) {
     constexpr int B = 1 << W;
     constexpr int T = kHistThreads;
     constexpr int U = kHistUnroll;
-    extern __shared__ uint32_t s_hist[];  // [P][B]
-    __shared__ uint32_t s_flags;
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [P][B][32]
     __shared__ uint32_t s_last;
     __shared__ uint32_t s_warp_tot[32];
 
     const int P = P_CT ? P_CT : a.passes.count;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lt = lanemask_lt();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    for (int i = tid; i < P * B; i += T) s_hist[i] = 0;
-    if (tid == 0) s_flags = a.agg_init;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_hist);
+        for (int i = tid; i < P * B * 8; i += T) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
 
     // Side job: clear the look-back descriptors the digit passes will use.
@@ -42,20 +45,14 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const HistArgs a) {
             a.zero_ptr[i] = z;
     }
 
-    uint32_t flags = a.agg_init;
-
-    auto tally = [&](uint32_t key, uint32_t warp_mask) {
+    uint32_t *col = s_hist + lane;  // this lane's column
+    auto tally = [&](uint32_t key) {
 #pragma unroll
         for (int p = 0; p < (P_CT ? P_CT : kMaxPasses); ++p) {
             if (!P_CT && p >= P) break;
             const uint32_t d = P_CT ? ((key >> (p * W)) & (B - 1))
                                     : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
-            if (flags & (1u << p)) {  // warp-uniform
-                const uint32_t peers = __match_any_sync(warp_mask, d);
-                if ((peers & lt) == 0) atomicAdd(&s_hist[p * B + d], (uint32_t)__popc(peers));
-            } else {
-                atomicAdd(&s_hist[p * B + d], 1u);
-            }
+            atomicAdd(col + ((p * B + d) << 5), 1u);
         }
     };
 
@@ -67,9 +64,7 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const HistArgs a) {
     const uint64_t n_vec = (a.n - head) >> 2;
     const uint64_t tail_start = head + (n_vec << 2);
 
-    uint32_t iter = 0;
-    for (uint64_t base = (uint64_t)blockIdx.x * (T * U); base < n_vec;
-         base += (uint64_t)gridDim.x * (T * U), ++iter) {
+    for (uint64_t base = (uint64_t)blockIdx.x * (T * U); base < n_vec; base += (uint64_t)gridDim.x * (T * U)) {
         uint4 v[U];
         bool ok[U];
 #pragma unroll
@@ -80,35 +75,24 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const HistArgs a) {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t m = __ballot_sync(0xffffffffu, ok[u]);
             if (ok[u]) {
-                tally(v[u].x, m);
-                tally(v[u].y, m);
-                tally(v[u].z, m);
-                tally(v[u].w, m);
+                tally(v[u].x);
+                tally(v[u].y);
+                tally(v[u].z);
+                tally(v[u].w);
             }
-        }
-        if ((iter & 3u) == 0u) {
-            // Re-evaluate the counting mode on the cumulative CTA histogram.
-            __syncthreads();
-            const uint32_t seen = (iter + 1u) * (uint32_t)(T * U * 4);
-            const uint32_t thr = seen >> 3;
-            for (int i = tid; i < P * B; i += T)
-                if (s_hist[i] > thr) atomicOr(&s_flags, 1u << (i / B));
-            __syncthreads();
-            flags = s_flags;
         }
     }
     if (blockIdx.x == 0) {
-        flags = 0;  // ragged ends: plain atomics, no warp-wide participation needed
-        if (tid < head) tally(a.keys[tid], 0);
-        if (tail_start + tid < a.n) tally(a.keys[tail_start + tid], 0);
+        if (tid < head) tally(a.keys[tid]);
+        if (tail_start + tid < a.n) tally(a.keys[tail_start + tid]);
     }
     __syncthreads();
 
-    for (int i = tid; i < P * B; i += T) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&a.ghist[i], c);
+    // Reduce the 32 lane columns of every (pass, bin) row and add the row to the global histogram.
+    for (int row = warp; row < P * B; row += T / 32) {
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, s_hist[(row << 5) + lane]);
+        if (lane == 0 && sum) atomicAdd(&a.ghist[row], sum);
     }
     __threadfence();
     __syncthreads();

@@ -16,10 +16,11 @@ constexpr int P_UNIFORM = (32 + W - 1) / W;
 
 template <int V, bool PAIRS, bool DST>
 cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
-    constexpr PassGeometry g = kGeometry[V];
+    constexpr PassVariant g = kVariants[V];
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
-    using TR = PassTraits<W, g.threads, ITEMS, PAIRS, DST>;
-    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, PAIRS, DST>;
+    constexpr int TB = g.table_bits < 1 ? 1 : g.table_bits;
+    using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
+    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, PAIRS, DST>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -35,11 +36,25 @@ template <int V>
 cudaError_t launch_modes(bool pairs, bool dst, const PassArgs &a, cudaStream_t s) {
     if (!pairs && !dst) return launch_variant<V, false, false>(a, s);
     if (pairs && !dst) return launch_variant<V, true, false>(a, s);
-    if constexpr (V == 0) {
-        if (!pairs && dst) return launch_variant<0, false, true>(a, s);
-        return launch_variant<0, true, true>(a, s);
+    if constexpr (V <= 1) {
+        if (!pairs && dst) return launch_variant<V, false, true>(a, s);
+        return launch_variant<V, true, true>(a, s);
     }
     return cudaErrorInvalidValue;
+}
+
+template <int P_CT>
+cudaError_t launch_hist_impl(const HistArgs &a, int passes, int grid, cudaStream_t s) {
+    auto kernel = hist_kernel<W, P_CT>;
+    const size_t smem = hist_smem_bytes(passes, W);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kernel<<<grid, kHistThreads, smem, s>>>(a);
+    return cudaGetLastError();
 }
 }  // namespace
 
@@ -47,27 +62,39 @@ cudaError_t launch_modes(bool pairs, bool dst, const PassArgs &a, cudaStream_t s
 #define B200_CAT(a, b) B200_CAT2(a, b)
 
 cudaError_t B200_CAT(launch_hist_w, B200_W)(bool uniform, const HistArgs &a, int grid, cudaStream_t s) {
-    const size_t smem = (size_t)(uniform ? P_UNIFORM : a.passes.count) * (1u << W) * sizeof(uint32_t);
-    if (uniform)
-        hist_kernel<W, P_UNIFORM><<<grid, kHistThreads, smem, s>>>(a);
-    else
-        hist_kernel<W, 0><<<grid, kHistThreads, smem, s>>>(a);
-    return cudaGetLastError();
+    if (uniform) return launch_hist_impl<P_UNIFORM>(a, P_UNIFORM, grid, s);
+    return launch_hist_impl<0>(a, a.passes.count, grid, s);
 }
 
 cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, const PassArgs &a,
                                             cudaStream_t s) {
-    if (dst) variant = 0;
+    if (dst && variant > 1) variant = 0;
     switch (variant) {
     case 0: return launch_modes<0>(pairs, dst, a, s);
-#if B200_W == 8
     case 1: return launch_modes<1>(pairs, dst, a, s);
+#if B200_W == 8
     case 2: return launch_modes<2>(pairs, dst, a, s);
     case 3: return launch_modes<3>(pairs, dst, a, s);
     case 4: return launch_modes<4>(pairs, dst, a, s);
+    case 5: return launch_modes<5>(pairs, dst, a, s);
+    case 6: return launch_modes<6>(pairs, dst, a, s);
+    case 7: return launch_modes<7>(pairs, dst, a, s);
+    case 8: return launch_modes<8>(pairs, dst, a, s);
+    case 9: return launch_modes<9>(pairs, dst, a, s);
+    case 10: return launch_modes<10>(pairs, dst, a, s);
+    case 11: return launch_modes<11>(pairs, dst, a, s);
+    case 12: return launch_modes<12>(pairs, dst, a, s);
+    case 13: return launch_modes<13>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }
 }
+
+#if B200_W == 8
+cudaError_t run_atomic_order_selftest(uint32_t *d_counter, int blocks, int rounds, cudaStream_t s) {
+    atomic_order_selftest<0><<<blocks, 256, 0, s>>>(d_counter, rounds, 0x5EED1234u);
+    return cudaGetLastError();
+}
+#endif
 
 }  // namespace b200sort

@@ -5,32 +5,46 @@
 
 namespace b200sort {
 
-// Digit-pass kernel geometries.  Variant 0 is the default and exists for every width; the
-// others are tuning alternatives instantiated for the 8-bit digit only.
-struct PassGeometry {
+// Digit-pass kernel variants: tile geometry x rank mode (see onesweep.cuh).  Variant 0 is the
+// default and exists for every width; the others are tuning alternatives instantiated for the
+// 8-bit digit only.  mode: 0 = RANK_TABLE, 1 = RANK_ATOMIC, 2 = RANK_MATCH.
+struct PassVariant {
     int threads;
     int items_keys;
     int items_pairs;
     int min_ctas;
+    int mode;
+    int table_bits;
 };
-constexpr int kNumVariants = 5;
-constexpr PassGeometry kGeometry[kNumVariants] = {
-    {384, 20, 14, 2},
-    {512, 15, 10, 2},
-    {256, 24, 16, 3},
-    {384, 16, 12, 2},
-    {512, 12, 8, 2},
+constexpr int kNumVariants = 14;
+constexpr PassVariant kVariants[kNumVariants] = {
+    {384, 20, 14, 3, 0, 5},   //  0 default: table(5 bits) + 3 ballots
+    {384, 20, 14, 3, 1, 0},   //  1 atomic rank
+    {256, 30, 20, 4, 0, 5},   //  2
+    {256, 30, 20, 4, 1, 0},   //  3
+    {512, 15, 10, 2, 0, 5},   //  4
+    {512, 15, 10, 2, 1, 0},   //  5
+    {384, 20, 14, 3, 0, 8},   //  6 full-digit atomicOr table, no ballots
+    {384, 20, 14, 3, 0, 6},   //  7 table(6 bits) + 2 ballots
+    {384, 20, 14, 2, 2, 0},   //  8 match.any (legacy, for the record)
+    {384, 16, 12, 4, 1, 0},   //  9
+    {384, 16, 12, 4, 0, 5},   // 10
+    {256, 24, 16, 5, 1, 0},   // 11
+    {256, 24, 16, 5, 0, 5},   // 12
+    {512, 12, 8, 3, 1, 0},    // 13
 };
 inline int tile_keys(int variant, bool pairs) {
-    const PassGeometry &g = kGeometry[variant];
+    const PassVariant &g = kVariants[variant];
     return g.threads * (pairs ? g.items_pairs : g.items_keys);
 }
+inline int variant_mode(int variant) { return kVariants[variant].mode; }
 // Smallest tile over all variants: bounds the descriptor array when sizing temp storage.
 constexpr int kMinTileKeys = 2048;
 
 // true if (width, variant) is instantiated; callers fall back to variant 0 otherwise.
+// Every width also carries variant 1 (same geometry as 0, atomic rank).
 inline bool variant_available(int width, int variant) {
-    return variant == 0 || (width == 8 && variant > 0 && variant < kNumVariants);
+    return variant == 0 || variant == 1 || (width == 8 && variant > 0 && variant < kNumVariants);
 }
 
 #define B200_DECLARE_W(w)                                                                        \
@@ -46,5 +60,10 @@ B200_DECLARE_W(6)
 B200_DECLARE_W(7)
 B200_DECLARE_W(8)
 #undef B200_DECLARE_W
+
+// Runs the RANK_ATOMIC self test on the current device; *mismatches = number of violations.
+cudaError_t run_atomic_order_selftest(uint32_t *d_counter, int blocks, int rounds, cudaStream_t s);
+// Dynamic shared memory of the histogram kernel for `passes` passes of 2^width bins.
+inline size_t hist_smem_bytes(int passes, int width) { return (size_t)passes * (1u << width) * 32 * 4; }
 
 }  // namespace b200sort

@@ -1,6 +1,6 @@
-// onesweep.cuh -- the digit-pass kernel: ONE kernel per digit that ranks a tile of keys,
-// resolves the tile's global bin offsets with a single-pass decoupled look-back, and writes
-// the keys (and values) to their final place for this digit.
+// onesweep.cuh -- the digit-pass kernel: ONE kernel per digit that counts and ranks a tile of
+// keys, resolves the tile's global bin offsets with a single-pass decoupled look-back, and
+// writes the keys (and values) to their final place for this digit.
 //
 // It replaces, per digit pass of the reference's sortByDevice loop
 // (SourceCode/Parallel7.cu:561-622):
@@ -13,59 +13,98 @@
 // descriptors until it meets an inclusive prefix.  scan[t][d] of the reference
 // (SourceCode/Baseline4.cu:127-138) == bin_base[d] + exclusive look-back prefix of (t, d).
 //
-// Stability: a tile covers TILE consecutive keys; warp w owns a contiguous slice of it and
-// loads it warp-striped (item i of lane l = slice[i*32 + l]); items are ranked in increasing
-// i, lanes inside a match.any group in increasing lane, warps in increasing w, tiles in
-// increasing tile id (dynamic ids from an atomic ticket, so a tile's predecessors are always
-// resident or finished -> the look-back cannot deadlock).
+// Tile schedule (B200 leaves ~16 SM cycles per 32 keys per pass at 70 % of HBM bandwidth, so
+// the design minimises shared-memory wavefronts and issue slots):
+//   1. load      warp-striped LDG: warp w owns a contiguous slice, item i of lane l =
+//                slice[i*32 + l]; every warp load is one 128-byte line
+//   2. count     s_cnt[warp][digit] += 1 with shared atomics (no return value)
+//   3. offsets   thread d: tile count of bin d = sum over warps -> publish AGGREGATE
+//                descriptor; block scan -> bin start in the tile; s_cnt[w][d] becomes the tile
+//                position of the first key of (warp w, bin d); look-back -> global base
+//   4. rank      tile position of every key, in stable order (three interchangeable modes,
+//                below), key stored at that position in shared memory
+//   5. write     thread t copies tile positions t, t+THREADS, ...: inside a bin run consecutive
+//                threads write consecutive destination words
 //
-// Descriptor status codes rotate with the launch parity so a descriptor array is cleared
-// once per sort, not once per pass: parity e uses NOT_READY = 2e, AGGREGATE = 2e+1,
-// INCLUSIVE = 2e+2 (mod 4); every descriptor ends a launch as INCLUSIVE(e) == NOT_READY(e+1).
+// Stable order inside (warp, digit): item index, then lane.  Rank modes:
+//   RANK_TABLE   peers of a lane = lanes of the same warp instruction with the same digit, found
+//                with one shared atomicOr + one load on a small per-warp table indexed by the
+//                digit's high TB bits (32 entries -> bank-conflict free) AND'ed with ballots on
+//                the remaining low bits; the highest peer fetches the run's base with ONE
+//                shared atomicAdd(count) (distinct addresses -> fully defined) and broadcasts it.
+//   RANK_ATOMIC  position = atomicAdd(&s_cnt[warp][digit], 1) by every lane.  Needs same-address
+//                shared atomics of one warp instruction to be applied in ascending lane order;
+//                PTX does not promise that, so the host only selects this mode after the
+//                on-device self test (atomic_order_selftest) passes.
+//   RANK_MATCH   match.any.sync peers (the textbook form).  Kept for the record: MATCH.ANY
+//                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.6 ms per pass.
+//
+// Tiles take dynamic ids from an atomic ticket, so a tile's predecessors are always resident
+// or finished and the look-back cannot deadlock.  Descriptor status codes rotate with the
+// launch parity so the descriptor array is cleared once per sort, not once per pass: parity e
+// uses NOT_READY = 2e, AGGREGATE = 2e+1, INCLUSIVE = 2e+2 (mod 4); every descriptor ends a
+// launch as INCLUSIVE(e) == NOT_READY(e+1).
 #pragma once
 #include "common.cuh"
 
 namespace b200sort {
 
-template <int W, int THREADS, int ITEMS, bool PAIRS, bool DST>
+enum RankMode { RANK_TABLE = 0, RANK_ATOMIC = 1, RANK_MATCH = 2 };
+
+template <int W, int THREADS, int ITEMS, int MODE, int TB, bool PAIRS, bool DST>
 struct PassTraits {
     static constexpr int B = 1 << W;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * ITEMS;
-    // s_keys[TILE] | s_whist[WARPS][B] | s_gbase[B or 2B] | (DST && PAIRS: s_vbase[2B]) | s_warp_tot[32]
-    static constexpr int SMEM_WORDS = TILE + WARPS * B + (DST ? 2 * B : B) + ((DST && PAIRS) ? 2 * B : 0) + 32;
+    static constexpr int NBALLOT = (MODE == RANK_TABLE && W > TB) ? W - TB : 0;
+    static constexpr int TABLE = (MODE == RANK_TABLE) ? (1 << (W - NBALLOT)) : 0;  // entries per mask table
+    // s_keys[TILE] | s_vals[TILE] (pairs) | s_cnt[WARPS][B] | s_gbase[B or 2B] | s_vbase[2B] (DST pairs)
+    // | s_mask[WARPS][2][TABLE] | s_warp_tot[32]
+    static constexpr int SMEM_WORDS = TILE + (PAIRS ? TILE : 0) + WARPS * B + (DST ? 2 * B : B) +
+                                      ((DST && PAIRS) ? 2 * B : 0) + WARPS * 2 * TABLE + 32;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
 };
 
-template <int W, int THREADS, int ITEMS, int MIN_CTAS, bool PAIRS, bool DST>
+template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
-    using TR = PassTraits<W, THREADS, ITEMS, PAIRS, DST>;
+    using TR = PassTraits<W, THREADS, ITEMS, MODE, TB, PAIRS, DST>;
     constexpr int B = TR::B;
     constexpr int WARPS = TR::WARPS;
     constexpr int TILE = TR::TILE;
     constexpr int WARP_KEYS = 32 * ITEMS;
+    constexpr int NBALLOT = TR::NBALLOT;
+    constexpr int TABLE = TR::TABLE;
     static_assert(B <= THREADS, "one thread per bin");
     static_assert(TILE < (1 << 16), "tile positions must fit 16 bits");
 
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_keys = smem;
-    uint32_t *s_whist = s_keys + TILE;
-    uint32_t *s_gbase = s_whist + WARPS * B;
+    uint32_t *s_vals = s_keys + TILE;
+    uint32_t *s_cnt = s_vals + (PAIRS ? TILE : 0);
+    uint32_t *s_gbase = s_cnt + WARPS * B;
     uint32_t *s_vbase = s_gbase + (DST ? 2 * B : B);
-    uint32_t *s_warp_tot = s_vbase + ((DST && PAIRS) ? 2 * B : 0);
+    uint32_t *s_mask = s_vbase + ((DST && PAIRS) ? 2 * B : 0);
+    uint32_t *s_warp_tot = s_mask + WARPS * 2 * TABLE;
     __shared__ uint32_t s_tile;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    for (int i = tid; i < WARPS * B; i += THREADS) s_whist[i] = 0;
+    {
+        // s_cnt .. s_mask are contiguous and start 16-byte aligned; rounding the vector count up
+        // spills at most 3 words into s_warp_tot, which is written before it is read.
+        uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
+        constexpr int ZV = (WARPS * B + (DST ? 2 * B : B) + ((DST && PAIRS) ? 2 * B : 0) + WARPS * 2 * TABLE + 3) / 4;
+        for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
+    const uint32_t shift = a.shift, mask = a.mask;
 
-    // ---- load: warp-striped, every warp load instruction is one 128-byte line ----------
+    // ---- 1. load ----------------------------------------------------------------------------
     uint32_t key[ITEMS];
     const uint32_t woff = warp * WARP_KEYS + lane;
     {
@@ -81,43 +120,29 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                 key[i] = (woff + i * 32 < n_valid) ? ld_stream(src + i * 32) : 0xFFFFFFFFu;
         }
     }
-
-    // ---- rank inside the warp: match.any groups + a warp-private running histogram -----
-    uint32_t rank[ITEMS];  // becomes the tile position of the key
-    {
-        uint32_t *wh = s_whist + warp * B;
-        const uint32_t lt = lanemask_lt();
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t d = (key[i] >> a.shift) & a.mask;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t below = peers & lt;
-            uint32_t old = 0;
-            if (below == 0) {  // lowest lane of the group owns the counter update
-                old = wh[d];
-                wh[d] = old + (uint32_t)__popc(peers);
-            }
-            __syncwarp();
-            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-            rank[i] = old + (uint32_t)__popc(below);
-        }
-    }
-
     uint32_t val[PAIRS ? ITEMS : 1];
     if (PAIRS) {
-        // Issue the value loads now; they land while the block scans and looks back.
         const uint32_t *vsrc = a.vals_in + tile_base + woff;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
             val[i] = (full || woff + i * 32 < n_valid) ? ld_stream(vsrc + i * 32) : 0u;
     }
+
+    // ---- 2. count ---------------------------------------------------------------------------
+    uint32_t *wcnt = s_cnt + warp * B;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) atomicAdd(wcnt + ((key[i] >> shift) & mask), 1u);
     __syncthreads();
 
-    // ---- tile histogram = sum over warps; publish it as early as possible --------------
+    // ---- 3. offsets -------------------------------------------------------------------------
     uint32_t count = 0;
+    uint32_t c[WARPS];
     if (tid < B) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) count += s_whist[w * B + tid];
+        for (int w = 0; w < WARPS; ++w) {
+            c[w] = s_cnt[w * B + tid];
+            count += c[w];
+        }
     }
     const uint32_t st_not = ((2u * a.parity) & 3u) << 30;
     const uint32_t st_agg = ((2u * a.parity + 1u) & 3u) << 30;
@@ -125,20 +150,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t *my_desc = a.desc + (size_t)tile * B + tid;
     if (tid < B) st_relaxed_gpu(my_desc, (tile == 0 ? st_inc : st_agg) | count);
 
-    // ---- bin starts inside the tile, then per-(warp, bin) tile positions ----------------
     const uint32_t bin_start = block_exclusive_scan<THREADS>(count, s_warp_tot);
     if (tid < B) {
         uint32_t run = bin_start;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s_whist[w * B + tid];
-            s_whist[w * B + tid] = run;
-            run += c;
+            s_cnt[w * B + tid] = run;
+            run += c[w];
         }
-    }
-
-    // ---- decoupled look-back: one thread per bin ----------------------------------------
-    if (tid < B) {
+        // decoupled look-back: one thread per bin
         uint32_t excl = 0;
         if (tile != 0) {
             const uint32_t *p = my_desc - B;
@@ -165,64 +185,113 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     }
     __syncthreads();
 
-    // ---- reorder through shared memory so each bin's keys are contiguous ----------------
-    {
-        const uint32_t *wh = s_whist + warp * B;
+    // ---- 4. rank + reorder through shared memory ----------------------------------------------
+    if (MODE == RANK_ATOMIC) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t d = (key[i] >> a.shift) & a.mask;
-            rank[i] += wh[d];
-            s_keys[rank[i]] = key[i];
+            const uint32_t pos = atomicAdd(wcnt + ((key[i] >> shift) & mask), 1u);
+            s_keys[pos] = key[i];
+            if (PAIRS) s_vals[pos] = val[i];
+        }
+    } else {
+        const uint32_t lt = lanemask_lt();
+        const uint32_t lanebit = 1u << lane;
+        uint32_t *wmask = s_mask + warp * 2 * TABLE;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = (key[i] >> shift) & mask;
+            uint32_t peers;
+            if (MODE == RANK_MATCH) {
+                peers = __match_any_sync(0xffffffffu, d);
+            } else {
+                uint32_t *row = wmask + (i & 1) * TABLE;  // two tables alternate: no clear/set race
+                const uint32_t hi = d >> NBALLOT;
+                atomicOr(row + hi, lanebit);
+                __syncwarp();
+                peers = row[hi];
+#pragma unroll
+                for (int b = 0; b < NBALLOT; ++b) {
+                    const uint32_t sb = 0u - ((d >> b) & 1u);  // 0 or ~0
+                    const uint32_t bal = __ballot_sync(0xffffffffu, sb != 0u);
+                    peers &= ~(bal ^ sb);
+                }
+                __syncwarp();
+                row[hi] = 0;
+            }
+            const uint32_t below = peers & lt;
+            uint32_t base = 0;
+            if ((peers >> lane) == 1u)  // highest lane of the group
+                base = atomicAdd(wcnt + d, (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
+            const uint32_t pos = base + (uint32_t)__popc(below);
+            s_keys[pos] = key[i];
+            if (PAIRS) s_vals[pos] = val[i];
         }
     }
     __syncthreads();
 
-    // ---- write out: consecutive threads -> consecutive tile positions -> (mostly)
-    //      consecutive destination addresses inside a bin run ------------------------------
-    uint32_t gpos[PAIRS ? ITEMS : 1];          // destination index (or offset) per written item
-    uint32_t dpack[(PAIRS && DST) ? (ITEMS + 3) / 4 : 1];
-    if (PAIRS && DST) {
-#pragma unroll
-        for (int q = 0; q < (ITEMS + 3) / 4; ++q) dpack[q] = 0;
-    }
+    // ---- 5. write out -------------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t j = tid + k * THREADS;
         if (full || j < n_valid) {
             const uint32_t kk = s_keys[j];
-            const uint32_t d = (kk >> a.shift) & a.mask;
+            const uint32_t d = (kk >> shift) & mask;
             if (!DST) {
                 const uint32_t g = s_gbase[d] + j;
                 a.keys_out[g] = kk;
-                if (PAIRS) gpos[k] = g;
+                if (PAIRS) a.vals_out[g] = s_vals[j];
             } else {
-                const uint64_t addr = reinterpret_cast<const uint64_t *>(s_gbase)[d] + 4ull * j;
-                *reinterpret_cast<uint32_t *>(addr) = kk;
-                if (PAIRS) dpack[k >> 2] |= d << (8 * (k & 3));
+                const uint64_t off = 4ull * j;
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk;
+                if (PAIRS)
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = s_vals[j];
             }
         }
     }
+}
 
-    if (PAIRS) {
-        __syncthreads();  // all keys read back from s_keys
+// ---- self test for RANK_ATOMIC ------------------------------------------------------------------
+// Every warp replays `rounds` random digit patterns (with heavy duplication) against a private
+// table and checks that atomicAdd(&table[d], 1) returned, for every lane, the number of earlier
+// items plus the number of LOWER lanes of the same instruction with the same digit.
+// mismatches[0] counts violations.
+template <int UNUSED>  // template only so the header can be included in several translation units
+__global__ void __launch_bounds__(256) atomic_order_selftest(uint32_t *mismatches, int rounds, uint32_t seed) {
+    __shared__ uint32_t table[8][256];
+    __shared__ uint32_t shadow[8][256];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; shadow[warp][i] = 0; }
+    __syncwarp();
+    uint32_t x = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
+    uint32_t bad = 0;
+    const uint32_t lt = lanemask_lt();
+    for (int r = 0; r < rounds; ++r) {
+        x = x * 1664525u + 1013904223u;
+        // digit spread varies per round: 1, 2, 4, ..., 256 distinct values
+        const uint32_t spread = (1u << (r % 9)) - 1u;
+        const uint32_t d = (x >> 13) & spread & 255u;
+        const uint32_t got = atomicAdd(&table[warp][d], 1u);
+        __syncwarp();
+        // reference rank by ballots over the 8 digit bits
+        uint32_t peers = 0xffffffffu;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) s_keys[rank[i]] = val[i];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t j = tid + k * THREADS;
-            if (full || j < n_valid) {
-                const uint32_t vv = s_keys[j];
-                if (!DST) {
-                    a.vals_out[gpos[k]] = vv;
-                } else {
-                    const uint32_t d = (dpack[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                    const uint64_t addr = reinterpret_cast<const uint64_t *>(s_vbase)[d] + 4ull * j;
-                    *reinterpret_cast<uint32_t *>(addr) = vv;
-                }
-            }
+        for (int b = 0; b < 8; ++b) {
+            const uint32_t sb = 0u - ((d >> b) & 1u);
+            const uint32_t bal = __ballot_sync(0xffffffffu, sb != 0u);
+            peers &= ~(bal ^ sb);
+        }
+        const uint32_t want = shadow[warp][d] + (uint32_t)__popc(peers & lt);
+        __syncwarp();
+        if ((peers >> lane) == 1u) shadow[warp][d] += (uint32_t)__popc(peers);
+        __syncwarp();
+        if (got != want) ++bad;
+        if ((r & 63) == 63) {  // keep counters small
+            for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; shadow[warp][i] = 0; }
+            __syncwarp();
         }
     }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace b200sort

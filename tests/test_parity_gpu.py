@@ -160,18 +160,41 @@ def test_multi_launch_portions(rs, oracle):
         rs.set_param("portion_tiles", 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", list(range(14)))
 def test_kernel_variants(rs, oracle, variant):
     rs.set_param("variant", variant)
     try:
+        assert variant < rs.get_param("num_variants")
         n = (1 << 20) + 12345
         k = oracle.generate("uniform", n)
         assert np.array_equal(dev_sort(rs, k, 8), oracle.sort_keys(k, 8))
+        z = oracle.generate("zipf", n)
+        assert np.array_equal(dev_sort(rs, z, 8), oracle.sort_keys(z, 8))
         kk = k & 0x3FF
         v = np.arange(n, dtype=np.uint32)
         ko, vo = rs.sort_pairs(to_dev(kk), to_dev(v), 8)
         rk, rv = oracle.sort_pairs(kk, v, 8)
         assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv)
+    finally:
+        rs.set_param("variant", 0)
+
+
+def test_atomic_rank_selftest_and_stability(rs, oracle):
+    """RANK_ATOMIC relies on lane-ordered same-address shared atomics; the library only uses it
+    after its on-device self test passed.  Whatever the verdict, variant 1 must stay stable."""
+    verdict = rs.get_param("atomic_rank_ok")
+    assert verdict in (0, 1)
+    rs.set_param("variant", 1)
+    try:
+        assert rs.get_param("effective_variant") == (1 if verdict == 1 else 0)
+        for kind in ("unique16", "all_equal", "zipf"):
+            n = 300007
+            k = oracle.generate(kind, n)
+            v = np.arange(n, dtype=np.uint32)
+            for nbits in (8, 4, 1):
+                ko, vo = rs.sort_pairs(to_dev(k), to_dev(v), nbits)
+                rk, rv = oracle.sort_pairs(k, v, nbits)
+                assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv), (kind, nbits)
     finally:
         rs.set_param("variant", 0)
 
