@@ -85,6 +85,8 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 11: return launch_modes<11>(pairs, dst, a, s);
     case 12: return launch_modes<12>(pairs, dst, a, s);
     case 13: return launch_modes<13>(pairs, dst, a, s);
+    case 14: return launch_modes<14>(pairs, dst, a, s);
+    case 15: return launch_modes<15>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -18,12 +18,15 @@
 //   1. load      warp-striped LDG: warp w owns a contiguous slice, item i of lane l =
 //                slice[i*32 + l]; every warp load is one 128-byte line
 //   2. count     s_cnt[warp][digit] += 1 with shared atomics (no return value)
-//   3. offsets   thread d: tile count of bin d = sum over warps -> publish AGGREGATE
-//                descriptor; block scan -> bin start in the tile; s_cnt[w][d] becomes the tile
-//                position of the first key of (warp w, bin d); look-back -> global base
-//   4. rank      tile position of every key, in stable order (three interchangeable modes,
-//                below), key stored at that position in shared memory
-//   5. write     thread t copies tile positions t, t+THREADS, ...: inside a bin run consecutive
+//   3. offsets   thread d: tile count of bin d = sum over warps -> publish the AGGREGATE
+//                descriptor; block scan -> bin start in the tile; s_cnt[w][d] becomes the
+//                shared-memory ADDRESS of the first key of (warp w, bin d)
+//   4. rank      address of every key in stable order (three interchangeable modes, below);
+//                the key is stored there, so each bin's keys end up contiguous
+//   5. look-back thread d walks the predecessors' descriptors of bin d, four at a time, then
+//                publishes the INCLUSIVE descriptor.  Placed after (4) so that predecessors
+//                have had the whole rank phase to publish.
+//   6. write     thread t copies tile positions t, t+THREADS, ...: inside a bin run consecutive
 //                threads write consecutive destination words
 //
 // Stable order inside (warp, digit): item index, then lane.  Rank modes:
@@ -32,12 +35,12 @@
 //                digit's high TB bits (32 entries -> bank-conflict free) AND'ed with ballots on
 //                the remaining low bits; the highest peer fetches the run's base with ONE
 //                shared atomicAdd(count) (distinct addresses -> fully defined) and broadcasts it.
-//   RANK_ATOMIC  position = atomicAdd(&s_cnt[warp][digit], 1) by every lane.  Needs same-address
+//   RANK_ATOMIC  address = atomicAdd(&s_cnt[warp][digit], 4) by every lane.  Needs same-address
 //                shared atomics of one warp instruction to be applied in ascending lane order;
 //                PTX does not promise that, so the host only selects this mode after the
 //                on-device self test (atomic_order_selftest) passes.
 //   RANK_MATCH   match.any.sync peers (the textbook form).  Kept for the record: MATCH.ANY
-//                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.6 ms per pass.
+//                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.4 ms per pass.
 //
 // Tiles take dynamic ids from an atomic ticket, so a tile's predecessors are always resident
 // or finished and the look-back cannot deadlock.  Descriptor status codes rotate with the
@@ -51,6 +54,28 @@ namespace b200sort {
 
 enum RankMode { RANK_TABLE = 0, RANK_ATOMIC = 1, RANK_MATCH = 2 };
 
+// ---- shared-memory accesses by 32-bit shared address (keeps address arithmetic to one LOP3) ----
+__device__ __forceinline__ void sm_inc(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void sm_or(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t sm_add_ret(uint32_t addr, uint32_t v) {
+    uint32_t r;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t sm_ld(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ void sm_st(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
+}
+
 template <int W, int THREADS, int ITEMS, int MODE, int TB, bool PAIRS, bool DST>
 struct PassTraits {
     static constexpr int B = 1 << W;
@@ -58,12 +83,21 @@ struct PassTraits {
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int NBALLOT = (MODE == RANK_TABLE && W > TB) ? W - TB : 0;
     static constexpr int TABLE = (MODE == RANK_TABLE) ? (1 << (W - NBALLOT)) : 0;  // entries per mask table
-    // s_keys[TILE] | s_vals[TILE] (pairs) | s_cnt[WARPS][B] | s_gbase[B or 2B] | s_vbase[2B] (DST pairs)
-    // | s_mask[WARPS][2][TABLE] | s_warp_tot[32]
-    static constexpr int SMEM_WORDS = TILE + (PAIRS ? TILE : 0) + WARPS * B + (DST ? 2 * B : B) +
-                                      ((DST && PAIRS) ? 2 * B : 0) + WARPS * 2 * TABLE + 32;
+    // word offsets inside dynamic shared memory (base is 1024-byte aligned; every table starts
+    // on a multiple of its own size so `base | offset` replaces `base + offset`)
+    static constexpr int OFF_KEYS = 0;
+    static constexpr int OFF_VALS = TILE;
+    static constexpr int OFF_CNT = OFF_VALS + (PAIRS ? TILE : 0);        // [WARPS][B]
+    static constexpr int OFF_GBASE = OFF_CNT + WARPS * B;                 // [B] or [B] x 64 bit
+    static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);       // [B] x 64 bit (DST pairs)
+    static constexpr int OFF_MASK = OFF_VBASE + ((DST && PAIRS) ? 2 * B : 0);  // [WARPS][2][TABLE]
+    static constexpr int OFF_MISC = OFF_MASK + WARPS * 2 * TABLE;         // warp totals[32] + tile id
+    static constexpr int SMEM_WORDS = OFF_MISC + 36;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
+    static_assert(TILE % B == 0, "tables must stay aligned to their size");
 };
+
+constexpr int kLookbackBatch = 4;
 
 template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
@@ -77,61 +111,70 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     static_assert(B <= THREADS, "one thread per bin");
     static_assert(TILE < (1 << 16), "tile positions must fit 16 bits");
 
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_keys = smem;
-    uint32_t *s_vals = s_keys + TILE;
-    uint32_t *s_cnt = s_vals + (PAIRS ? TILE : 0);
-    uint32_t *s_gbase = s_cnt + WARPS * B;
-    uint32_t *s_vbase = s_gbase + (DST ? 2 * B : B);
-    uint32_t *s_mask = s_vbase + ((DST && PAIRS) ? 2 * B : 0);
-    uint32_t *s_warp_tot = s_mask + WARPS * 2 * TABLE;
-    __shared__ uint32_t s_tile;
+    extern __shared__ __align__(1024) uint32_t smem[];
+    uint32_t *s_keys = smem + TR::OFF_KEYS;
+    uint32_t *s_vals = smem + TR::OFF_VALS;
+    uint32_t *s_cnt = smem + TR::OFF_CNT;
+    uint32_t *s_gbase = smem + TR::OFF_GBASE;
+    uint32_t *s_vbase = smem + TR::OFF_VBASE;
+    uint32_t *s_warp_tot = smem + TR::OFF_MISC;
+    uint32_t *s_tile = smem + TR::OFF_MISC + 32;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t sa_keys = smem_u32(s_keys);
+    const uint32_t sa_wcnt = smem_u32(s_cnt + warp * B);  // multiple of 4*B bytes
 
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    if (tid == 0) *s_tile = atomicAdd(a.ticket, 1u);
     {
-        // s_cnt .. s_mask are contiguous and start 16-byte aligned; rounding the vector count up
-        // spills at most 3 words into s_warp_tot, which is written before it is read.
+        // s_cnt .. s_mask are contiguous and 16-byte aligned; rounding the vector count up spills
+        // at most 3 words into s_warp_tot, which is written before it is read.
         uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
-        constexpr int ZV = (WARPS * B + (DST ? 2 * B : B) + ((DST && PAIRS) ? 2 * B : 0) + WARPS * 2 * TABLE + 3) / 4;
+        constexpr int ZV = (TR::OFF_MISC - TR::OFF_CNT + 3) / 4;
         for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t tile = *s_tile;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
-    const uint32_t shift = a.shift, mask = a.mask;
+    // byte offset of a key's digit inside a 4-byte-entry table: (rotr(key, shift-2) & mask4)
+    const uint32_t rot = (a.shift + 30u) & 31u;
+    const uint32_t mask4 = a.mask << 2;
 
     // ---- 1. load ----------------------------------------------------------------------------
     uint32_t key[ITEMS];
-    const uint32_t woff = warp * WARP_KEYS + lane;
-    {
-        const uint32_t *src = a.keys_in + tile_base + woff;
-        if (full) {
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) key[i] = ld_stream(src + i * 32);
-        } else {
-            // Out-of-range items become all-ones keys: they fall in the highest occupied bin,
-            // after every real key of the tile, i.e. at tile positions >= n_valid.
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i)
-                key[i] = (woff + i * 32 < n_valid) ? ld_stream(src + i * 32) : 0xFFFFFFFFu;
-        }
-    }
     uint32_t val[PAIRS ? ITEMS : 1];
-    if (PAIRS) {
-        const uint32_t *vsrc = a.vals_in + tile_base + woff;
+    const uint32_t woff = warp * WARP_KEYS + lane;
+    if (full) {
+        const uint32_t *src = a.keys_in + tile_base + woff;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i)
-            val[i] = (full || woff + i * 32 < n_valid) ? ld_stream(vsrc + i * 32) : 0u;
+        for (int i = 0; i < ITEMS; ++i) key[i] = ld_stream(src + i * 32);
+        if (PAIRS) {
+            const uint32_t *vsrc = a.vals_in + tile_base + woff;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) val[i] = ld_stream(vsrc + i * 32);
+        }
+    } else {
+        // Ragged last tile (once per launch): staged through shared memory so that the path above
+        // stays free of per-item predicates.  Out-of-range items become all-ones keys: they fall
+        // in the highest occupied bin, after every real key of the tile, i.e. at tile positions
+        // >= n_valid, and are never written out.
+#pragma unroll 1
+        for (uint32_t j = tid; j < (uint32_t)TILE; j += THREADS) {
+            s_keys[j] = (j < n_valid) ? a.keys_in[tile_base + j] : 0xFFFFFFFFu;
+            if (PAIRS) s_vals[j] = (j < n_valid) ? a.vals_in[tile_base + j] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            key[i] = s_keys[woff + i * 32];
+            if (PAIRS) val[i] = s_vals[woff + i * 32];
+        }
     }
 
     // ---- 2. count ---------------------------------------------------------------------------
-    uint32_t *wcnt = s_cnt + warp * B;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) atomicAdd(wcnt + ((key[i] >> shift) & mask), 1u);
+    for (int i = 0; i < ITEMS; ++i) sm_inc(sa_wcnt | (__funnelshift_r(key[i], key[i], rot) & mask4));
     __syncthreads();
 
     // ---- 3. offsets -------------------------------------------------------------------------
@@ -152,24 +195,83 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 
     const uint32_t bin_start = block_exclusive_scan<THREADS>(count, s_warp_tot);
     if (tid < B) {
-        uint32_t run = bin_start;
+        // RANK_ATOMIC keeps ready-to-use shared addresses; the other modes keep tile positions
+        uint32_t run = (MODE == RANK_ATOMIC) ? sa_keys + 4u * bin_start : bin_start;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
             s_cnt[w * B + tid] = run;
-            run += c[w];
+            run += (MODE == RANK_ATOMIC) ? 4u * c[w] : c[w];
         }
-        // decoupled look-back: one thread per bin
+    }
+    __syncthreads();
+
+    // ---- 4. rank + reorder through shared memory ----------------------------------------------
+    if (MODE == RANK_ATOMIC) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t at = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i], key[i], rot) & mask4), 4u);
+            sm_st<0>(at, key[i]);
+            if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+        }
+    } else {
+        const uint32_t lt = lanemask_lt();
+        const uint32_t lanebit = 1u << lane;
+        const uint32_t sa_wmask = smem_u32(smem + TR::OFF_MASK + warp * 2 * TABLE);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d4 = __funnelshift_r(key[i], key[i], rot) & mask4;
+            uint32_t peers;
+            if (MODE == RANK_MATCH) {
+                peers = __match_any_sync(0xffffffffu, d4);
+            } else {
+                // two tables alternate so that clearing one never races with filling the next
+                const uint32_t row = sa_wmask + (uint32_t)(i & 1) * (TABLE * 4);
+                const uint32_t slot = row + ((d4 >> NBALLOT) & ~3u);
+                sm_or(slot, lanebit);
+                __syncwarp();
+                peers = sm_ld(slot);
+#pragma unroll
+                for (int b = 0; b < NBALLOT; ++b) {
+                    const bool bit = (d4 & (4u << b)) != 0u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
+                __syncwarp();
+                sm_st<0>(slot, 0u);
+            }
+            uint32_t base = 0;
+            if ((peers >> lane) == 1u)  // highest lane of the group
+                base = sm_add_ret(sa_wcnt | d4, (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
+            const uint32_t at = sa_keys + 4u * (base + (uint32_t)__popc(peers & lt));
+            sm_st<0>(at, key[i]);
+            if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+        }
+    }
+
+    // ---- 5. decoupled look-back: one thread per bin, kLookbackBatch descriptors in flight ------
+    if (tid < B) {
         uint32_t excl = 0;
         if (tile != 0) {
-            const uint32_t *p = my_desc - B;
-            while (true) {
-                uint32_t v;
-                do {
-                    v = ld_relaxed_gpu(p);
-                } while ((v & kDescFlagMask) == st_not);
-                excl += v & kDescValueMask;
-                if ((v & kDescFlagMask) == st_inc) break;
-                p -= B;
+            const uint32_t *col = a.desc + tid;
+            int32_t t = (int32_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[kLookbackBatch];
+#pragma unroll
+                for (int k = 0; k < kLookbackBatch; ++k)
+                    v[k] = (t - k >= 0) ? ld_relaxed_gpu(col + (size_t)(t - k) * B) : st_inc;
+                bool stop = false;
+#pragma unroll
+                for (int k = 0; k < kLookbackBatch; ++k) {
+                    const uint32_t f = v[k] & kDescFlagMask;
+                    if (!stop && f == st_not) stop = true;  // not published yet: poll again from here
+                    if (!stop) {
+                        excl += v[k] & kDescValueMask;
+                        --t;
+                        if (f == st_inc) { stop = true; done = true; }
+                    }
+                }
             }
             st_relaxed_gpu(my_desc, st_inc | (excl + count));
         }
@@ -185,101 +287,77 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     }
     __syncthreads();
 
-    // ---- 4. rank + reorder through shared memory ----------------------------------------------
-    if (MODE == RANK_ATOMIC) {
+    // ---- 6. write out -------------------------------------------------------------------------
+    const uint32_t sa_gbase = smem_u32(s_gbase);
+    uint32_t *const kout = a.keys_out;
+    uint32_t *const vout = a.vals_out;
+    if (full) {
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t pos = atomicAdd(wcnt + ((key[i] >> shift) & mask), 1u);
-            s_keys[pos] = key[i];
-            if (PAIRS) s_vals[pos] = val[i];
-        }
-    } else {
-        const uint32_t lt = lanemask_lt();
-        const uint32_t lanebit = 1u << lane;
-        uint32_t *wmask = s_mask + warp * 2 * TABLE;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t d = (key[i] >> shift) & mask;
-            uint32_t peers;
-            if (MODE == RANK_MATCH) {
-                peers = __match_any_sync(0xffffffffu, d);
-            } else {
-                uint32_t *row = wmask + (i & 1) * TABLE;  // two tables alternate: no clear/set race
-                const uint32_t hi = d >> NBALLOT;
-                atomicOr(row + hi, lanebit);
-                __syncwarp();
-                peers = row[hi];
-#pragma unroll
-                for (int b = 0; b < NBALLOT; ++b) {
-                    const uint32_t sb = 0u - ((d >> b) & 1u);  // 0 or ~0
-                    const uint32_t bal = __ballot_sync(0xffffffffu, sb != 0u);
-                    peers &= ~(bal ^ sb);
-                }
-                __syncwarp();
-                row[hi] = 0;
-            }
-            const uint32_t below = peers & lt;
-            uint32_t base = 0;
-            if ((peers >> lane) == 1u)  // highest lane of the group
-                base = atomicAdd(wcnt + d, (uint32_t)__popc(peers));
-            base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
-            const uint32_t pos = base + (uint32_t)__popc(below);
-            s_keys[pos] = key[i];
-            if (PAIRS) s_vals[pos] = val[i];
-        }
-    }
-    __syncthreads();
-
-    // ---- 5. write out -------------------------------------------------------------------------
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const uint32_t j = tid + k * THREADS;
-        if (full || j < n_valid) {
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t j = tid + k * THREADS;
             const uint32_t kk = s_keys[j];
-            const uint32_t d = (kk >> shift) & mask;
+            const uint32_t d4 = __funnelshift_r(kk, kk, rot) & mask4;
             if (!DST) {
-                const uint32_t g = s_gbase[d] + j;
-                a.keys_out[g] = kk;
-                if (PAIRS) a.vals_out[g] = s_vals[j];
+                const uint32_t g = sm_ld(sa_gbase | d4) + j;
+                kout[g] = kk;
+                if (PAIRS) vout[g] = s_vals[j];
             } else {
                 const uint64_t off = 4ull * j;
-                *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk;
+                *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d4 >> 2] + off) = kk;
                 if (PAIRS)
-                    *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = s_vals[j];
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d4 >> 2] + off) = s_vals[j];
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t j = tid + k * THREADS;
+            if (j < n_valid) {
+                const uint32_t kk = s_keys[j];
+                const uint32_t d4 = __funnelshift_r(kk, kk, rot) & mask4;
+                if (!DST) {
+                    const uint32_t g = sm_ld(sa_gbase | d4) + j;
+                    kout[g] = kk;
+                    if (PAIRS) vout[g] = s_vals[j];
+                } else {
+                    const uint64_t off = 4ull * j;
+                    *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d4 >> 2] + off) = kk;
+                    if (PAIRS)
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d4 >> 2] + off) = s_vals[j];
+                }
             }
         }
     }
 }
 
 // ---- self test for RANK_ATOMIC ------------------------------------------------------------------
-// Every warp replays `rounds` random digit patterns (with heavy duplication) against a private
-// table and checks that atomicAdd(&table[d], 1) returned, for every lane, the number of earlier
-// items plus the number of LOWER lanes of the same instruction with the same digit.
-// mismatches[0] counts violations.
+// Every warp replays `rounds` random digit patterns (from 1 to 256 distinct values per
+// instruction) against a private table and checks that atom.shared.add returned, for every
+// lane, the number of earlier items plus the number of LOWER lanes of the same instruction with
+// the same digit.  mismatches[0] counts violations.
 template <int UNUSED>  // template only so the header can be included in several translation units
 __global__ void __launch_bounds__(256) atomic_order_selftest(uint32_t *mismatches, int rounds, uint32_t seed) {
-    __shared__ uint32_t table[8][256];
+    __shared__ __align__(1024) uint32_t table[8][256];
     __shared__ uint32_t shadow[8][256];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; shadow[warp][i] = 0; }
     __syncwarp();
+    const uint32_t sa_table = smem_u32(&table[warp][0]);
     uint32_t x = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
     uint32_t bad = 0;
     const uint32_t lt = lanemask_lt();
     for (int r = 0; r < rounds; ++r) {
         x = x * 1664525u + 1013904223u;
-        // digit spread varies per round: 1, 2, 4, ..., 256 distinct values
-        const uint32_t spread = (1u << (r % 9)) - 1u;
+        const uint32_t spread = (1u << (r % 9)) - 1u;  // 1, 2, 4, ..., 256 distinct values
         const uint32_t d = (x >> 13) & spread & 255u;
-        const uint32_t got = atomicAdd(&table[warp][d], 1u);
+        const uint32_t got = sm_add_ret(sa_table | (d << 2), 4u) >> 2;
         __syncwarp();
-        // reference rank by ballots over the 8 digit bits
-        uint32_t peers = 0xffffffffu;
+        uint32_t peers = 0xffffffffu;  // reference rank by ballots over the 8 digit bits
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-            const uint32_t sb = 0u - ((d >> b) & 1u);
-            const uint32_t bal = __ballot_sync(0xffffffffu, sb != 0u);
-            peers &= ~(bal ^ sb);
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
         }
         const uint32_t want = shadow[warp][d] + (uint32_t)__popc(peers & lt);
         __syncwarp();
