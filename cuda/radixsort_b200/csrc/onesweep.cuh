@@ -42,8 +42,10 @@
 //   RANK_MATCH   match.any.sync peers (the textbook form).  Kept for the record: MATCH.ANY
 //                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.4 ms per pass.
 //
-// Tiles take dynamic ids from an atomic ticket, so a tile's predecessors are always resident
-// or finished and the look-back cannot deadlock.  Descriptor status codes rotate with the
+// Tile id = blockIdx.x: CTAs are dispatched in increasing block index, so a tile's predecessors
+// are always resident or finished when it spins on them (the same assumption CUB's decoupled
+// look-back scan makes); this saves one global atomic round trip at the head of every tile.
+// Descriptor status codes rotate with the
 // launch parity so the descriptor array is cleared once per sort, not once per pass: parity e
 // uses NOT_READY = 2e, AGGREGATE = 2e+1, INCLUSIVE = 2e+2 (mod 4); every descriptor ends a
 // launch as INCLUSIVE(e) == NOT_READY(e+1).
@@ -97,7 +99,7 @@ struct PassTraits {
     static_assert(TILE % B == 0, "tables must stay aligned to their size");
 };
 
-constexpr int kLookbackBatch = 4;
+constexpr int kLookbackBatch = 8;
 
 template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
@@ -118,13 +120,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t *s_gbase = smem + TR::OFF_GBASE;
     uint32_t *s_vbase = smem + TR::OFF_VBASE;
     uint32_t *s_warp_tot = smem + TR::OFF_MISC;
-    uint32_t *s_tile = smem + TR::OFF_MISC + 32;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t sa_keys = smem_u32(s_keys);
     const uint32_t sa_wcnt = smem_u32(s_cnt + warp * B);  // multiple of 4*B bytes
 
-    if (tid == 0) *s_tile = atomicAdd(a.ticket, 1u);
     {
         // s_cnt .. s_mask are contiguous and 16-byte aligned; rounding the vector count up spills
         // at most 3 words into s_warp_tot, which is written before it is read.
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    const uint32_t tile = *s_tile;
+    const uint32_t tile = blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
