@@ -100,6 +100,7 @@ struct PassTraits {
 };
 
 constexpr int kLookbackBatch = 8;
+constexpr int kGroup = 6;  // shared-memory operations in flight per thread in the rank / write-out loops
 
 template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
@@ -207,11 +208,21 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
     if (MODE == RANK_ATOMIC) {
+        // Software-pipelined in groups: kGroup atomics in flight before their dependent stores,
+        // so a warp pays one shared-memory round trip per group instead of one per key.
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t at = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i], key[i], rot) & mask4), 4u);
-            sm_st<0>(at, key[i]);
-            if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+        for (int i0 = 0; i0 < ITEMS; i0 += kGroup) {
+            uint32_t at[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g)
+                if (i0 + g < ITEMS)
+                    at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), 4u);
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g)
+                if (i0 + g < ITEMS) {
+                    sm_st<0>(at[g], key[i0 + g]);
+                    if (PAIRS) sm_st<TILE * 4>(at[g], val[i0 + g]);
+                }
         }
     } else {
         const uint32_t lt = lanemask_lt();
@@ -293,19 +304,33 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t *const vout = a.vals_out;
     if (full) {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t j = tid + k * THREADS;
-            const uint32_t kk = s_keys[j];
-            const uint32_t d4 = __funnelshift_r(kk, kk, rot) & mask4;
+        for (int k0 = 0; k0 < ITEMS; k0 += kGroup) {
+            uint32_t kk[kGroup], gb[kGroup];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g)
+                if (k0 + g < ITEMS) kk[g] = sm_ld(sa_keys + 4u * (tid + (k0 + g) * THREADS));
             if (!DST) {
-                const uint32_t g = sm_ld(sa_gbase | d4) + j;
-                kout[g] = kk;
-                if (PAIRS) vout[g] = s_vals[j];
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g)
+                    if (k0 + g < ITEMS) gb[g] = sm_ld(sa_gbase | (__funnelshift_r(kk[g], kk[g], rot) & mask4));
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g)
+                    if (k0 + g < ITEMS) {
+                        const uint32_t j = tid + (k0 + g) * THREADS;
+                        kout[gb[g] + j] = kk[g];
+                        if (PAIRS) vout[gb[g] + j] = s_vals[j];
+                    }
             } else {
-                const uint64_t off = 4ull * j;
-                *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d4 >> 2] + off) = kk;
-                if (PAIRS)
-                    *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d4 >> 2] + off) = s_vals[j];
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g)
+                    if (k0 + g < ITEMS) {
+                        const uint32_t j = tid + (k0 + g) * THREADS;
+                        const uint32_t d = (__funnelshift_r(kk[g], kk[g], rot) & mask4) >> 2;
+                        const uint64_t off = 4ull * j;
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk[g];
+                        if (PAIRS)
+                            *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = s_vals[j];
+                    }
             }
         }
     } else {
