@@ -24,7 +24,7 @@ thread_local std::string g_last_error = "";
 std::atomic<uint64_t> g_launches{0};
 
 struct Params {
-    int variant = 0;
+    int variant = -1;  // -1 = automatic choice (see effective_variant)
     int portion_tiles = 0;  // 0 = as many as fit the 30-bit descriptor value
     int hist_ctas_per_sm = 2;
 } g_params;
@@ -165,8 +165,14 @@ int run_selftest() {
     return g_atomic_rank_ok;
 }
 
+// Automatic choice: the fastest measured geometry (profiles/r01_sweep_*.jsonl) in atomic-rank mode
+// when the device passed the self test, else the table-rank default.
+constexpr int kAutoVariantW8 = 10;
+
 int effective_variant(int width) {
-    int v = variant_available(width, g_params.variant) ? g_params.variant : 0;
+    int v = g_params.variant;
+    if (v < 0) v = (width == 8) ? kAutoVariantW8 : 1;
+    if (!variant_available(width, v)) v = 0;
     if (variant_mode(v) == 1 && !run_selftest()) {
         // same geometry, table rank: variants are laid out as (table, atomic) twins where possible
         v = (v >= 1 && variant_mode(v - 1) == 0 && kVariants[v - 1].threads == kVariants[v].threads &&
@@ -440,7 +446,7 @@ size_t b200sort_temp_bytes(uint64_t n, int nBits, int pairs) {
 int b200sort_set_param(const char *name, int value) {
     if (!name) return B200SORT_EINVAL;
     if (!strcmp(name, "variant")) {
-        if (value < 0 || value >= kNumVariants) return B200SORT_EINVAL;
+        if (value < -1 || value >= kNumVariants) return B200SORT_EINVAL;
         g_params.variant = value;
         return 0;
     }
@@ -463,7 +469,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "portion_tiles")) return g_params.portion_tiles;
     if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
     if (!strcmp(name, "num_variants")) return kNumVariants;
-    if (!strcmp(name, "effective_variant")) return check_device() ? g_params.variant : effective_variant(8);
+    if (!strcmp(name, "effective_variant")) return check_device() ? std::max(g_params.variant, 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
     return B200SORT_EINVAL;
 }

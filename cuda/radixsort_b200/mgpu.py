@@ -1,0 +1,306 @@
+"""Sharded sort over 2/4/8 GPUs: one process per GPU, torch.distributed (NCCL over NVLink 5 /
+NVSwitch) for the plumbing, libb200sort kernels for every byte of compute.
+
+The reference has nothing multi-GPU; the parity target is
+"concatenation of the shards in rank order == sortByHost of the whole input".
+
+    top-digit histogram (b200sort_histogram, 8 bits)            local,  4 B/key read
+    all_gather of the G x 256 count matrix                      16 KiB, latency bound
+    splitters = top-digit bin boundaries nearest to j*N/G       host, identical on every rank
+    MSD partition = ONE stable digit pass on the top digit      local,  8 B/key
+        - exchange=nccl : into a local buffer, then one all_to_all_single over NVLink
+        - exchange=fused: the digit-pass kernel stores every bin straight into the owning
+          rank's receive buffer (symmetric memory, peer pointers) -- partition and exchange
+          are one kernel, the NVLink transfer overlaps the ranking tile by tile
+    local LSD sort of the received bucket (b200sort_keys)        local,  36 B/key
+
+Receive offsets are ordered by source rank and every step is stable, so equal keys keep their
+global input order (matters for the key/value variant).
+
+`ops` abstracts the device kernels so that the orchestration (everything in this file) can be
+exercised on CPU with the gloo backend in tests (tests/test_mgpu_cpu.py supplies numpy ops);
+the product always uses DeviceOps.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+TOP_BITS = 8
+
+
+# ---------------------------------------------------------------------------------------------
+# pure host logic (unit-tested on CPU)
+
+def choose_owner(global_hist: np.ndarray, world: int) -> np.ndarray:
+    """owner[b] = rank that receives top-digit bin b.  Boundaries are the bin edges closest to
+    the ideal cut points j*N/world, so owners are non-decreasing in b and every rank gets a
+    contiguous range of bins (possibly empty for heavily skewed inputs)."""
+    bins = global_hist.size
+    total = int(global_hist.sum())
+    csum = np.concatenate([[0], np.cumsum(global_hist.astype(np.int64))])  # csum[b] = keys in bins < b
+    cuts = [0]
+    for j in range(1, world):
+        target = j * total / world
+        b = int(np.searchsorted(csum, target, side="left"))
+        b = min(max(b, 0), bins)
+        if b > 0 and abs(csum[b - 1] - target) <= abs(csum[b] - target):
+            b -= 1
+        cuts.append(max(b, cuts[-1]))
+    cuts.append(bins)
+    owner = np.empty(bins, dtype=np.int64)
+    for r in range(world):
+        owner[cuts[r]:cuts[r + 1]] = r
+    return owner
+
+
+def plan_exchange(counts_all: np.ndarray, rank: int):
+    """counts_all[src][bin] -> everything a rank needs for the exchange.
+
+    Returns dict with owner[bin], send_counts[dst], recv_counts[src], recv_offsets[src] (where
+    src's keys start in my receive buffer), my_total, and bin_recv_offset[bin]: the offset, in
+    the OWNER's receive buffer, where this rank's keys of `bin` start (used by the fused path)."""
+    counts_all = np.asarray(counts_all, dtype=np.int64)
+    world, bins = counts_all.shape
+    owner = choose_owner(counts_all.sum(axis=0), world)
+    matrix = np.zeros((world, world), dtype=np.int64)  # matrix[src][dst]
+    for dst in range(world):
+        matrix[:, dst] = counts_all[:, owner == dst].sum(axis=1)
+    send_counts = matrix[rank].copy()
+    recv_counts = matrix[:, rank].copy()
+    recv_offsets = np.concatenate([[0], np.cumsum(recv_counts)[:-1]])
+    # offset of (rank, bin) inside owner's buffer = keys from lower source ranks for that owner
+    #                                             + this rank's keys of earlier bins of the same owner
+    src_base = np.zeros(world, dtype=np.int64)  # src_base[dst] = sum_{s < rank} matrix[s][dst]
+    if rank > 0:
+        src_base = matrix[:rank].sum(axis=0)
+    bin_recv_offset = np.zeros(bins, dtype=np.int64)
+    running = src_base.copy()
+    for b in range(bins):
+        d = owner[b]
+        bin_recv_offset[b] = running[d]
+        running[d] += counts_all[rank, b]
+    return {"owner": owner, "matrix": matrix, "send_counts": send_counts, "recv_counts": recv_counts,
+            "recv_offsets": recv_offsets, "my_total": int(recv_counts.sum()),
+            "bin_recv_offset": bin_recv_offset, "totals": matrix.sum(axis=0)}
+
+
+# ---------------------------------------------------------------------------------------------
+class DeviceOps:
+    """The product's device operations: libb200sort through the C ABI."""
+
+    def __init__(self):
+        from . import api
+        self.api = api
+        self.ws = api.Workspace("cuda")
+
+    def histogram(self, keys, shift, bits):
+        return self.api.histogram(keys, shift, bits, workspace=self.ws)
+
+    def digit_pass(self, keys, shift, bits, out=None, bin_dst=None):
+        return self.api.digit_pass(keys, shift, bits, out_keys=out, bin_dst=bin_dst, workspace=self.ws)
+
+    def sort(self, keys, nbits, out):
+        return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
+
+    def empty(self, n):
+        return torch.empty(n, dtype=torch.int32, device="cuda")
+
+
+class PhaseTimer:
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+
+    def report(self):
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+class ShardedSorter:
+    """Sorts a uint32 array that is sharded over the ranks of `group` (keys only)."""
+
+    def __init__(self, group=None, per_rank_capacity: int = 0, nbits: int = 8, fused: bool = False,
+                 ops=None, time_phases: bool = True):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.nbits = nbits
+        self.ops = ops if ops is not None else DeviceOps()
+        self.on_gpu = ops is None
+        self.capacity = int(per_rank_capacity)
+        self.fused = bool(fused) and self.on_gpu
+        self.timer = PhaseTimer(time_phases and self.on_gpu)
+        self.last_plan = None
+        self.recv = None
+        self.peer_ptrs = None
+        self.symm = None
+        self.part = None
+        self.out = None
+        if self.capacity:
+            self._allocate(self.capacity)
+
+    # -- buffers ------------------------------------------------------------------------------
+    def _allocate(self, capacity: int):
+        self.capacity = capacity
+        if self.fused:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.recv = symm_mem.empty(capacity, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+                self.symm = symm_mem.rendezvous(self.recv, self.group.group_name)
+                self.peer_ptrs = [int(p) for p in self.symm.buffer_ptrs]
+            except Exception as e:  # symmetric memory unavailable: NCCL exchange
+                self.fused = False
+                self.fused_error = repr(e)
+        if not self.fused:
+            self.recv = self.ops.empty(capacity)
+        self.out = self.ops.empty(capacity)
+
+    # -- the sort -----------------------------------------------------------------------------
+    def sort(self, keys):
+        """keys: this rank's shard (4-byte ints).  Returns this rank's slice of the globally sorted
+        array (a view of an internal buffer, valid until the next call)."""
+        ops, world, rank = self.ops, self.world, self.rank
+        n_local = keys.numel()
+        shift = 32 - TOP_BITS
+        t = self.timer
+        t.marks = []
+        t.mark("start")
+
+        hist = ops.histogram(keys, shift, TOP_BITS)                     # device, uint32 counts as int32
+        t.mark("histogram")
+        counts = hist.to(torch.int64) & 0xFFFFFFFF
+        gathered = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
+        dist.all_gather_into_tensor(gathered, counts, group=self.group)
+        counts_all = gathered.cpu().numpy().reshape(world, -1)          # sync point: split sizes live on the host
+        plan = plan_exchange(counts_all, rank)
+        self.last_plan = plan
+        need = int(plan["totals"].max())
+        if self.recv is None or need > self.capacity:
+            if self.fused and self.recv is not None:
+                raise RuntimeError(f"receive capacity {self.capacity} < {need}: construct ShardedSorter with a larger per_rank_capacity")
+            self._allocate(max(need, int(n_local * 1.05) + 1024))
+        t.mark("splitters")
+
+        my_total = plan["my_total"]
+        if self.fused:
+            # partition + exchange in one kernel: every bin is stored straight into its owner's buffer
+            addr = np.array([self.peer_ptrs[int(o)] for o in plan["owner"]], dtype=np.int64) + 4 * plan["bin_recv_offset"]
+            bin_dst = torch.from_numpy(addr).to("cuda")
+            self.symm.barrier(channel=0)        # peers are done reading their previous receive buffers
+            ops.digit_pass(keys, shift, TOP_BITS, bin_dst=bin_dst)
+            self.symm.barrier(channel=1)        # every rank's stores have landed
+            t.mark("partition+exchange")
+        else:
+            if self.part is None or self.part.numel() < n_local:
+                self.part = ops.empty(n_local)
+            part = ops.digit_pass(keys, shift, TOP_BITS, out=self.part[:n_local])
+            t.mark("partition")
+            self._all_to_all(self.recv[:my_total], part, plan["recv_counts"], plan["send_counts"])
+            t.mark("exchange")
+
+        out = self.out[:my_total]
+        if my_total:
+            ops.sort(self.recv[:my_total], self.nbits, out)
+        t.mark("local_sort")
+        return out
+
+    def _all_to_all(self, recv, send, recv_counts, send_counts):
+        rc = [int(c) for c in recv_counts]
+        sc = [int(c) for c in send_counts]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+            return
+        # gloo (CPU tests): point-to-point emulation of the same exchange
+        ro = np.concatenate([[0], np.cumsum(rc)]).astype(np.int64)
+        so = np.concatenate([[0], np.cumsum(sc)]).astype(np.int64)
+        ops_list = []
+        for peer in range(self.world):
+            if peer == self.rank:
+                recv[ro[peer]:ro[peer + 1]].copy_(send[so[peer]:so[peer + 1]])
+                continue
+            if sc[peer]:
+                ops_list.append(dist.P2POp(dist.isend, send[so[peer]:so[peer + 1]].contiguous(),
+                                           dist.get_global_rank(self.group, peer), group=self.group))
+            if rc[peer]:
+                ops_list.append(dist.P2POp(dist.irecv, recv[ro[peer]:ro[peer + 1]],
+                                           dist.get_global_rank(self.group, peer), group=self.group))
+        if ops_list:
+            for req in dist.batch_isend_irecv(ops_list):
+                req.wait()
+
+    # -- reporting ----------------------------------------------------------------------------
+    def phase_report(self) -> dict:
+        """Per-phase milliseconds of the LAST sort, max over ranks; plus exchange bytes / NVLink figure."""
+        local = self.timer.report()
+        if not local:
+            return {}
+        names = sorted(local)
+        vals = torch.tensor([local[k] for k in names], dtype=torch.float64, device="cuda")
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX, group=self.group)
+        rep = {k: float(v) for k, v in zip(names, vals.tolist())}
+        plan = self.last_plan
+        if plan is not None:
+            sent = int(plan["send_counts"].sum() - plan["send_counts"][self.rank]) * 4
+            rep["egress_bytes_this_rank"] = sent
+            key = "partition+exchange" if self.fused else "exchange"
+            if rep.get(key):
+                rep["egress_gbs_this_rank"] = sent / (rep[key] * 1e-3) / 1e9
+            rep["exchange"] = "fused peer stores" if self.fused else "nccl all_to_all_single"
+            rep["shard_sizes"] = [int(x) for x in plan["totals"]]
+        return rep
+
+
+# ---------------------------------------------------------------------------------------------
+def verify_sharded(result, keys, group=None, verify_fn=None) -> bool:
+    """Size-independent check of a sharded sort (used at 2^32 keys where no host can hold the
+    oracle's answer): every shard non-decreasing, shard boundaries ordered, total count kept and
+    the order-independent multiset fingerprint (sum key, sum sm64(key), xor sm64(key)) unchanged."""
+    group = group if group is not None else dist.group.WORLD
+    world = dist.get_world_size(group)
+    if verify_fn is None:
+        from . import api
+        verify_fn = api.verify
+    dev = result.device
+    bad, s1, h1, x1 = verify_fn(result) if result.numel() else (0, 0, 0, 0)
+    _, s0, h0, x0 = verify_fn(keys) if keys.numel() else (0, 0, 0, 0)
+    lo = int(result[0].item()) & 0xFFFFFFFF if result.numel() else -1
+    hi = int(result[-1].item()) & 0xFFFFFFFF if result.numel() else -1
+
+    def i64(v):  # two's-complement wrap into int64
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    mine = torch.tensor([bad, result.numel(), keys.numel(), i64(s1), i64(h1), i64(x1), i64(s0), i64(h0), i64(x0), lo, hi],
+                        dtype=torch.int64, device=dev)
+    allv = torch.empty(world * mine.numel(), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allv, mine, group=group)
+    rows = allv.cpu().numpy().reshape(world, -1)
+    ok = int(rows[:, 0].sum()) == 0 and int(rows[:, 1].sum()) == int(rows[:, 2].sum())
+    m = (1 << 64) - 1
+    ok &= (sum(int(v) for v in rows[:, 3]) & m) == (sum(int(v) for v in rows[:, 6]) & m)
+    ok &= (sum(int(v) for v in rows[:, 4]) & m) == (sum(int(v) for v in rows[:, 7]) & m)
+    x_out = x_in = 0
+    for r in range(world):
+        x_out ^= int(rows[r, 5]) & m
+        x_in ^= int(rows[r, 8]) & m
+    ok &= x_out == x_in
+    prev_hi = -1
+    for r in range(world):
+        if rows[r, 1] == 0:
+            continue
+        ok &= int(rows[r, 9]) >= prev_hi
+        prev_hi = int(rows[r, 10])
+    return bool(ok)

@@ -83,6 +83,7 @@ def test_argument_errors_without_touching_the_gpu(rs):
     assert lib.b200sort_keys_host(a.ctypes.data, 0, o.ctypes.data, 8, 512) == 0        # n == 0 no-op
     assert lib.b200sort_keys(None, 0, None, None, 0, 8, None) == 0
     assert lib.b200sort_set_param(b"variant", 99) == -1
+    assert lib.b200sort_set_param(b"variant", -1) == 0     # automatic choice
     assert lib.b200sort_set_param(b"no_such_param", 1) == -1
     assert b"invalid" in lib.b200sort_error_string(-1)
     assert lib.b200sort_version() == 100

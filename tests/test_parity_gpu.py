@@ -176,7 +176,7 @@ def test_kernel_variants(rs, oracle, variant):
         rk, rv = oracle.sort_pairs(kk, v, 8)
         assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv)
     finally:
-        rs.set_param("variant", 0)
+        rs.set_param("variant", -1)
 
 
 def test_atomic_rank_selftest_and_stability(rs, oracle):
@@ -187,6 +187,7 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
     rs.set_param("variant", 1)
     try:
         assert rs.get_param("effective_variant") == (1 if verdict == 1 else 0)
+        assert rs.get_param("atomic_rank_ok") == verdict
         for kind in ("unique16", "all_equal", "zipf"):
             n = 300007
             k = oracle.generate(kind, n)
@@ -196,7 +197,7 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
                 rk, rv = oracle.sort_pairs(k, v, nbits)
                 assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv), (kind, nbits)
     finally:
-        rs.set_param("variant", 0)
+        rs.set_param("variant", -1)
 
 
 def test_histogram_matches_tile_table_column_sums(rs, oracle):
