@@ -334,7 +334,7 @@ def run_multi(args):
     per = total // world
     keys = rs.generate("uniform", per, first=rank * per, total=total)
     sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * 1.02) + (1 << 20),
-                                nbits=args.nbits, fused=not args.no_fused)
+                                nbits=args.nbits, fused=not args.no_fused, allow_narrow=not args.no_narrow)
     result = None
     for _ in range(args.warmup):
         result = sorter.sort(keys)
@@ -387,6 +387,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true")
+    ap.add_argument("--no-narrow", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

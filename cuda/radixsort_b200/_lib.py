@@ -54,6 +54,7 @@ SIGNATURES = {
     "b200sort_tile_keys": (C.c_int, [C.c_int]),
     "b200sort_algorithmic_bytes": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),
     "b200sort_num_passes": (C.c_int, [C.c_int]),
+    "b200sort_device_banner": (C.c_int, [C.c_char_p, C.c_size_t]),
     "b200sort_version": (C.c_int, []),
     "b200sort_error_string": (C.c_char_p, [C.c_int]),
     "b200sort_last_error_string": (C.c_char_p, []),

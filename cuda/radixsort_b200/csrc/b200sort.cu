@@ -171,7 +171,7 @@ constexpr int kAutoVariantW8 = 10;
 
 int effective_variant(int width) {
     int v = g_params.variant;
-    if (v < 0) v = (width == 8) ? kAutoVariantW8 : 1;
+    if (v < 0) v = (width == 8) ? kAutoVariantW8 : (width <= 3 ? kBallotVariant : 1);
     if (!variant_available(width, v)) v = 0;
     if (variant_mode(v) == 1 && !run_selftest()) {
         // same geometry, table rank: variants are laid out as (table, atomic) twins where possible
@@ -555,7 +555,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     cudaStream_t s = (cudaStream_t)stream;
 
     int variant = effective_variant(bits);
-    if (dst && variant > 1) variant = 0;
+    if (dst && variant > 1 && variant != kBallotVariant) variant = variant_mode(variant) == 1 ? 1 : 0;
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);
     if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage");
@@ -634,6 +634,32 @@ int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void
     g_launches.fetch_add(1, std::memory_order_relaxed);
     verify_kernel<<<grid, 256, 0, s>>>(d_keys, n, reinterpret_cast<unsigned long long *>(d_result));
     CU(cudaGetLastError());
+    return 0;
+}
+
+int b200sort_device_banner(char *buf, size_t len) {
+    if (!buf || len == 0) return B200SORT_EINVAL;
+    int rc = check_device();
+    if (rc) return rc;
+    int dev = 0;
+    cudaDeviceProp p;
+    CU(cudaGetDevice(&dev));
+    CU(cudaGetDeviceProperties(&p, dev));
+    // same fields and layout as printDeviceInfo(), SourceCode/Parallel7.cu:664-677
+    snprintf(buf, len,
+             "**********GPU info**********\n"
+             "Name: %s\n"
+             "Compute capability: %d.%d\n"
+             "Num SMs: %d\n"
+             "Max num threads per SM: %d\n"
+             "Max num warps per SM: %d\n"
+             "GMEM: %zu byte\n"
+             "SMEM per SM: %zu byte\n"
+             "SMEM per block: %zu byte\n"
+             "****************************\n",
+             p.name, p.major, p.minor, p.multiProcessorCount, p.maxThreadsPerMultiProcessor,
+             p.maxThreadsPerMultiProcessor / p.warpSize, p.totalGlobalMem, p.sharedMemPerMultiprocessor,
+             p.sharedMemPerBlock);
     return 0;
 }
 

@@ -16,7 +16,7 @@ struct PassVariant {
     int mode;
     int table_bits;
 };
-constexpr int kNumVariants = 16;
+constexpr int kNumVariants = 17;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -34,6 +34,7 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {384, 32, 20, 3, 1, 0},   // 13
     {384, 24, 16, 3, 1, 0},   // 14
     {512, 30, 20, 2, 1, 0},   // 15
+    {256, 30, 20, 4, 0, 0},   // 16 ballots only (narrow digits); instantiated for every width
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
@@ -45,8 +46,10 @@ constexpr int kMinTileKeys = 2048;
 
 // true if (width, variant) is instantiated; callers fall back to variant 0 otherwise.
 // Every width also carries variant 1 (same geometry as 0, atomic rank).
+constexpr int kBallotVariant = 16;
 inline bool variant_available(int width, int variant) {
-    return variant == 0 || variant == 1 || (width == 8 && variant > 0 && variant < kNumVariants);
+    return variant == 0 || variant == 1 || variant == kBallotVariant ||
+           (width == 8 && variant > 0 && variant < kNumVariants);
 }
 
 #define B200_DECLARE_W(w)                                                                        \

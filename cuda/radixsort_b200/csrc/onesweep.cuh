@@ -39,6 +39,10 @@
 //                shared atomics of one warp instruction to be applied in ascending lane order;
 //                PTX does not promise that, so the host only selects this mode after the
 //                on-device self test (atomic_order_selftest) passes.
+//                With TB = 0 the table disappears and the ballots alone find the peers: the mode
+//                used for digits of <= 3 bits (2..8 bins), where almost every lane has peers
+//                and same-address atomics with a return value would serialise (measured: 18
+//                cycles per warp instruction at 2 distinct addresses, 32 at one).
 //   RANK_MATCH   match.any.sync peers (the textbook form).  Kept for the record: MATCH.ANY
 //                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.4 ms per pass.
 //
@@ -238,17 +242,23 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                 // two tables alternate so that clearing one never races with filling the next
                 const uint32_t row = sa_wmask + (uint32_t)(i & 1) * (TABLE * 4);
                 const uint32_t slot = row + ((d4 >> NBALLOT) & ~3u);
-                sm_or(slot, lanebit);
-                __syncwarp();
-                peers = sm_ld(slot);
+                if (TABLE > 1) {
+                    sm_or(slot, lanebit);
+                    __syncwarp();
+                    peers = sm_ld(slot);
+                } else {
+                    peers = 0xffffffffu;  // narrow digit: ballots alone identify the peers
+                }
 #pragma unroll
                 for (int b = 0; b < NBALLOT; ++b) {
                     const bool bit = (d4 & (4u << b)) != 0u;
                     const uint32_t bal = __ballot_sync(0xffffffffu, bit);
                     peers &= bit ? bal : ~bal;
                 }
-                __syncwarp();
-                sm_st<0>(slot, 0u);
+                if (TABLE > 1) {
+                    __syncwarp();
+                    sm_st<0>(slot, 0u);
+                }
             }
             uint32_t base = 0;
             if ((peers >> lane) == 1u)  // highest lane of the group

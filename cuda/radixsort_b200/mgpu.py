@@ -81,9 +81,19 @@ def plan_exchange(counts_all: np.ndarray, rank: int):
         d = owner[b]
         bin_recv_offset[b] = running[d]
         running[d] += counts_all[rank, b]
+    # Splitters that coincide with the top log2(world) bits (uniform keys on 2/4/8 ranks): the
+    # partition can then run as a log2(world)-bit digit pass -- 2..8 bins instead of 256, i.e.
+    # runs of thousands of keys per (tile, destination), which is what NVLink stores want.
+    lg = int(world).bit_length() - 1
+    narrow_bits = 0
+    if world > 1 and (1 << lg) == world and bins >= world:
+        shift = int(bins).bit_length() - 1 - lg
+        if np.array_equal(owner, np.arange(bins) >> shift):
+            narrow_bits = lg
     return {"owner": owner, "matrix": matrix, "send_counts": send_counts, "recv_counts": recv_counts,
             "recv_offsets": recv_offsets, "my_total": int(recv_counts.sum()),
-            "bin_recv_offset": bin_recv_offset, "totals": matrix.sum(axis=0)}
+            "bin_recv_offset": bin_recv_offset, "totals": matrix.sum(axis=0),
+            "src_base": src_base, "narrow_bits": narrow_bits}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -133,7 +143,7 @@ class ShardedSorter:
     """Sorts a uint32 array that is sharded over the ranks of `group` (keys only)."""
 
     def __init__(self, group=None, per_rank_capacity: int = 0, nbits: int = 8, fused: bool = False,
-                 ops=None, time_phases: bool = True):
+                 ops=None, time_phases: bool = True, allow_narrow: bool = True):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -142,6 +152,7 @@ class ShardedSorter:
         self.on_gpu = ops is None
         self.capacity = int(per_rank_capacity)
         self.fused = bool(fused) and self.on_gpu
+        self.allow_narrow = allow_narrow
         self.timer = PhaseTimer(time_phases and self.on_gpu)
         self.last_plan = None
         self.recv = None
@@ -195,18 +206,23 @@ class ShardedSorter:
         t.mark("splitters")
 
         my_total = plan["my_total"]
+        pbits = plan["narrow_bits"] if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
+        pshift = 32 - pbits
         if self.fused:
             # partition + exchange in one kernel: every bin is stored straight into its owner's buffer
-            addr = np.array([self.peer_ptrs[int(o)] for o in plan["owner"]], dtype=np.int64) + 4 * plan["bin_recv_offset"]
+            if pbits == TOP_BITS:
+                addr = np.array([self.peer_ptrs[int(o)] for o in plan["owner"]], dtype=np.int64) + 4 * plan["bin_recv_offset"]
+            else:
+                addr = np.array(self.peer_ptrs[:world], dtype=np.int64) + 4 * plan["src_base"]
             bin_dst = torch.from_numpy(addr).to("cuda")
             self.symm.barrier(channel=0)        # peers are done reading their previous receive buffers
-            ops.digit_pass(keys, shift, TOP_BITS, bin_dst=bin_dst)
+            ops.digit_pass(keys, pshift, pbits, bin_dst=bin_dst)
             self.symm.barrier(channel=1)        # every rank's stores have landed
             t.mark("partition+exchange")
         else:
             if self.part is None or self.part.numel() < n_local:
                 self.part = ops.empty(n_local)
-            part = ops.digit_pass(keys, shift, TOP_BITS, out=self.part[:n_local])
+            part = ops.digit_pass(keys, pshift, pbits, out=self.part[:n_local])
             t.mark("partition")
             self._all_to_all(self.recv[:my_total], part, plan["recv_counts"], plan["send_counts"])
             t.mark("exchange")
@@ -259,6 +275,7 @@ class ShardedSorter:
             if rep.get(key):
                 rep["egress_gbs_this_rank"] = sent / (rep[key] * 1e-3) / 1e9
             rep["exchange"] = "fused peer stores" if self.fused else "nccl all_to_all_single"
+            rep["partition_bits"] = int(plan["narrow_bits"]) if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
             rep["shard_sizes"] = [int(x) for x in plan["totals"]]
         return rep
 

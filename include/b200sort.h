@@ -149,6 +149,10 @@ int b200sort_tile_keys(int pairs);
 uint64_t b200sort_algorithmic_bytes(uint64_t n, int nBits, int pairs);
 int b200sort_num_passes(int nBits);
 
+/* Device banner in the layout of the reference's printDeviceInfo() (SourceCode/Parallel7.cu:
+ * 664-677), for drivers that reproduce its log. */
+int b200sort_device_banner(char *buf, size_t len);
+
 int b200sort_version(void);
 const char *b200sort_error_string(int code);
 const char *b200sort_last_error_string(void);

@@ -57,6 +57,21 @@ def test_plan_exchange_is_consistent_across_ranks():
         assert [x[2] for x in spans if x[1]] == sorted(x[2] for x in spans if x[1])   # grouped by source rank
 
 
+def test_narrow_partition_detection():
+    uniform = np.full((4, 256), 100)
+    assert mgpu.plan_exchange(uniform, 0)["narrow_bits"] == 2
+    assert mgpu.plan_exchange(np.full((2, 256), 7), 1)["narrow_bits"] == 1
+    assert mgpu.plan_exchange(np.full((8, 256), 7), 3)["narrow_bits"] == 3
+    skew = uniform.copy()
+    skew[:, :64] *= 5                       # splitters move off the 2-bit boundaries
+    p = mgpu.plan_exchange(skew, 2)
+    assert p["narrow_bits"] == 0
+    assert mgpu.plan_exchange(np.full((3, 256), 7), 0)["narrow_bits"] == 0    # not a power of two
+    # narrow plan offsets: src_base[d] is where this rank's keys start in rank d's buffer
+    p = mgpu.plan_exchange(uniform, 2)
+    assert np.array_equal(p["src_base"], uniform[:2].reshape(2, 4, 64).sum(axis=2).sum(axis=0))
+
+
 class NumpyOps:
     """numpy stand-ins for the device kernels (same contracts as include/b200sort.h)."""
 

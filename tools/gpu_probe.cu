@@ -57,6 +57,29 @@ __global__ void atoms_rate(uint32_t *sink, int iters, uint32_t seed, uint32_t ma
     if (h[threadIdx.x] == 0x12345678u) *sink = 1;
 }
 
+// shared-memory op rates under controlled address patterns: mode 0 red.add, 1 atom.add (return used),
+// 2 st.shared, 3 ld.shared.  `mask` limits the number of distinct addresses per warp instruction.
+__global__ void smem_rate(uint32_t *sink, int iters, uint32_t seed, uint32_t mask, int mode) {
+    __shared__ uint32_t h[32][256];
+    const uint32_t warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t x = (uint32_t)sm64(seed + threadIdx.x + blockIdx.x * 1024u), acc = 0;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(&h[warp][0]);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t a = base + (((x >> (u * 8)) & mask) << 2);
+            if (mode == 0) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+            else if (mode == 1) { uint32_t r; asm volatile("atom.shared.add.u32 %0, [%1], 4;" : "=r"(r) : "r"(a) : "memory"); acc += r; }
+            else if (mode == 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+            else { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); acc += r; }
+        }
+        x = x * 1664525u + 1013904223u;
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
 template <typename F> float time_ms(F f, int reps) {
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     f(); CK(cudaDeviceSynchronize());
@@ -106,6 +129,14 @@ int main(int argc, char **argv) {
         warp_instr = (double)blocks * (threads / 32) * iters * 4;
         printf(", \"atoms_mask%u_warp_instr_per_us_per_sm\": %.1f", mask, warp_instr / (ms * 1e3) / p.multiProcessorCount);
     }
+    const char *names[4] = {"red_add", "atom_add_ret", "st", "ld"};
+    for (int mode = 0; mode < 4; ++mode)
+        for (uint32_t mask : {255u, 15u, 1u, 0u}) {
+            ms = time_ms([&] { smem_rate<<<blocks, threads>>>(sink, iters, 1, mask, mode); }, 3);
+            warp_instr = (double)blocks * (threads / 32) * iters * 4;
+            printf(", \"smem_%s_mask%u_cycles_per_warp_instr\": %.2f", names[mode], mask,
+                   (ms * 1e-3) * (clk_khz * 1e3) * p.multiProcessorCount / warp_instr);
+        }
     printf(", \"clock_khz\": %d}\n", clk_khz);
     return 0;
 }
