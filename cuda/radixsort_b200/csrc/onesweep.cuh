@@ -64,8 +64,10 @@ enum RankMode { RANK_TABLE = 0, RANK_ATOMIC = 1, RANK_MATCH = 2 };
 __device__ __forceinline__ void sm_inc(uint32_t addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
+// Lanes OR disjoint bits into a cleared word, so an add is equivalent -- and red.shared.add combines
+// the lanes of one instruction that hit the same address, which the or form may serialise.
 __device__ __forceinline__ void sm_or(uint32_t addr, uint32_t v) {
-    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t sm_add_ret(uint32_t addr, uint32_t v) {
     uint32_t r;
@@ -97,7 +99,8 @@ struct PassTraits {
     static constexpr int OFF_GBASE = OFF_CNT + WARPS * B;                 // [B] or [B] x 64 bit
     static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);       // [B] x 64 bit (DST pairs)
     static constexpr int OFF_MASK = OFF_VBASE + ((DST && PAIRS) ? 2 * B : 0);  // [WARPS][2][TABLE]
-    static constexpr int OFF_MISC = OFF_MASK + WARPS * 2 * TABLE;         // warp totals[32] + tile id
+    static constexpr int OFF_HOT = OFF_MASK + WARPS * 2 * TABLE;          // [WARPS] hot digit of each warp (0 = none)
+    static constexpr int OFF_MISC = OFF_HOT + ((WARPS + 3) / 4) * 4;      // warp totals[32]
     static constexpr int SMEM_WORDS = OFF_MISC + 36;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
     static_assert(TILE % B == 0, "tables must stay aligned to their size");
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t *s_gbase = smem + TR::OFF_GBASE;
     uint32_t *s_vbase = smem + TR::OFF_VBASE;
     uint32_t *s_warp_tot = smem + TR::OFF_MISC;
+    uint32_t *s_hot = smem + TR::OFF_HOT;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t sa_keys = smem_u32(s_keys);
@@ -190,6 +194,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         for (int w = 0; w < WARPS; ++w) {
             c[w] = s_cnt[w * B + tid];
             count += c[w];
+            // A digit holding >= 1/4 of a warp's keys makes that warp "skewed": its rank loop
+            // combines the lanes of that digit before the atomic (see step 4).
+            if (MODE == RANK_ATOMIC && c[w] >= (uint32_t)(WARP_KEYS / 4)) s_hot[w] = (tid << 2) | 1u;
         }
     }
     const uint32_t st_not = ((2u * a.parity) & 3u) << 30;
@@ -212,21 +219,46 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
     if (MODE == RANK_ATOMIC) {
-        // Software-pipelined in groups: kGroup atomics in flight before their dependent stores,
-        // so a warp pays one shared-memory round trip per group instead of one per key.
+        const uint32_t hot = s_hot[warp];
+        if (hot == 0u) {
+            // Software-pipelined in groups: kGroup atomics in flight before their dependent stores,
+            // so a warp pays one shared-memory round trip per group instead of one per key.
 #pragma unroll
-        for (int i0 = 0; i0 < ITEMS; i0 += kGroup) {
-            uint32_t at[kGroup];
+            for (int i0 = 0; i0 < ITEMS; i0 += kGroup) {
+                uint32_t at[kGroup];
 #pragma unroll
-            for (int g = 0; g < kGroup; ++g)
-                if (i0 + g < ITEMS)
-                    at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), 4u);
+                for (int g = 0; g < kGroup; ++g)
+                    if (i0 + g < ITEMS)
+                        at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), 4u);
 #pragma unroll
-            for (int g = 0; g < kGroup; ++g)
-                if (i0 + g < ITEMS) {
-                    sm_st<0>(at[g], key[i0 + g]);
-                    if (PAIRS) sm_st<TILE * 4>(at[g], val[i0 + g]);
+                for (int g = 0; g < kGroup; ++g)
+                    if (i0 + g < ITEMS) {
+                        sm_st<0>(at[g], key[i0 + g]);
+                        if (PAIRS) sm_st<TILE * 4>(at[g], val[i0 + g]);
+                    }
+            }
+        } else {
+            // Skewed warp (sorted / few distinct / heavy-hitter inputs): atom.shared.add with a return
+            // value serialises lanes that share an address (32 cycles per instruction when all 32 do),
+            // so the lanes holding the warp's hot digit are ranked with one ballot and ONE atomic.
+            const uint32_t hot4 = hot & ~3u;
+            const uint32_t lt = lanemask_lt();
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t d4 = __funnelshift_r(key[i], key[i], rot) & mask4;
+                const bool is_hot = d4 == hot4;
+                const uint32_t hm = __ballot_sync(0xffffffffu, is_hot);
+                uint32_t at = 0;
+                if (!is_hot) {
+                    at = sm_add_ret(sa_wcnt | d4, 4u);
+                } else if ((hm & lt) == 0u) {  // lowest hot lane
+                    at = sm_add_ret(sa_wcnt | hot4, 4u * (uint32_t)__popc(hm));
                 }
+                const uint32_t lead = __shfl_sync(0xffffffffu, at, hm ? (__ffs(hm) - 1) : 0);
+                if (is_hot) at = lead + 4u * (uint32_t)__popc(hm & lt);
+                sm_st<0>(at, key[i]);
+                if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+            }
         }
     } else {
         const uint32_t lt = lanemask_lt();
