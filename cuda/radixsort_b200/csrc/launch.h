@@ -21,14 +21,14 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0},   //  1 atomic rank (selected only after the self test passes)
     {256, 36, 24, 4, 0, 5},   //  2
-    {256, 36, 24, 4, 1, 0},   //  3
+    {256, 36, 20, 4, 1, 0},   //  3
     {384, 20, 14, 3, 0, 5},   //  4
     {384, 20, 14, 3, 1, 0},   //  5
     {256, 30, 20, 4, 0, 8},   //  6 full-digit atomicOr table, no ballots
     {256, 30, 20, 4, 0, 6},   //  7 table(6 bits) + 2 ballots
     {384, 20, 14, 2, 2, 0},   //  8 match.any (for the record)
-    {256, 40, 26, 4, 1, 0},   //  9
-    {256, 44, 28, 3, 1, 0},   // 10
+    {256, 40, 24, 3, 1, 0},   //  9
+    {256, 44, 22, 3, 1, 0},   // 10
     {512, 36, 24, 2, 1, 0},   // 11
     {512, 24, 16, 3, 1, 0},   // 12
     {384, 32, 20, 3, 1, 0},   // 13

@@ -84,6 +84,15 @@ __device__ __forceinline__ void sm_st(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void sm_st2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 sm_ld2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+
 template <int W, int THREADS, int ITEMS, int MODE, int TB, bool PAIRS, bool DST>
 struct PassTraits {
     static constexpr int B = 1 << W;
@@ -93,8 +102,8 @@ struct PassTraits {
     static constexpr int TABLE = (MODE == RANK_TABLE) ? (1 << (W - NBALLOT)) : 0;  // entries per mask table
     // word offsets inside dynamic shared memory (base is 1024-byte aligned; every table starts
     // on a multiple of its own size so `base | offset` replaces `base + offset`)
-    static constexpr int OFF_KEYS = 0;
-    static constexpr int OFF_VALS = TILE;
+    static constexpr int OFF_KEYS = 0;   // keys: uint32[TILE]; pairs: {key, value}[TILE] (8-byte slots)
+    static constexpr int OFF_VALS = TILE;  // second half of the pair region (staging of a ragged tile only)
     static constexpr int OFF_CNT = OFF_VALS + (PAIRS ? TILE : 0);        // [WARPS][B]
     static constexpr int OFF_GBASE = OFF_CNT + WARPS * B;                 // [B] or [B] x 64 bit
     static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);       // [B] x 64 bit (DST pairs)
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     constexpr int TABLE = TR::TABLE;
     static_assert(B <= THREADS, "one thread per bin");
     static_assert(TILE < (1 << 16), "tile positions must fit 16 bits");
+    constexpr uint32_t kSlot = PAIRS ? 8u : 4u;  // bytes per reordered element in shared memory
 
     extern __shared__ __align__(1024) uint32_t smem[];
     uint32_t *s_keys = smem + TR::OFF_KEYS;
@@ -208,11 +218,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     const uint32_t bin_start = block_exclusive_scan<THREADS>(count, s_warp_tot);
     if (tid < B) {
         // RANK_ATOMIC keeps ready-to-use shared addresses; the other modes keep tile positions
-        uint32_t run = (MODE == RANK_ATOMIC) ? sa_keys + 4u * bin_start : bin_start;
+        uint32_t run = (MODE == RANK_ATOMIC) ? sa_keys + kSlot * bin_start : bin_start;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
             s_cnt[w * B + tid] = run;
-            run += (MODE == RANK_ATOMIC) ? 4u * c[w] : c[w];
+            run += (MODE == RANK_ATOMIC) ? kSlot * c[w] : c[w];
         }
     }
     __syncthreads();
@@ -229,12 +239,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
                     if (i0 + g < ITEMS)
-                        at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), 4u);
+                        at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), kSlot);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
                     if (i0 + g < ITEMS) {
-                        sm_st<0>(at[g], key[i0 + g]);
-                        if (PAIRS) sm_st<TILE * 4>(at[g], val[i0 + g]);
+                        if (PAIRS) sm_st2(at[g], key[i0 + g], val[i0 + g]);
+                        else sm_st<0>(at[g], key[i0 + g]);
                     }
             }
         } else {
@@ -250,14 +260,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                 const uint32_t hm = __ballot_sync(0xffffffffu, is_hot);
                 uint32_t at = 0;
                 if (!is_hot) {
-                    at = sm_add_ret(sa_wcnt | d4, 4u);
+                    at = sm_add_ret(sa_wcnt | d4, kSlot);
                 } else if ((hm & lt) == 0u) {  // lowest hot lane
-                    at = sm_add_ret(sa_wcnt | hot4, 4u * (uint32_t)__popc(hm));
+                    at = sm_add_ret(sa_wcnt | hot4, kSlot * (uint32_t)__popc(hm));
                 }
                 const uint32_t lead = __shfl_sync(0xffffffffu, at, hm ? (__ffs(hm) - 1) : 0);
-                if (is_hot) at = lead + 4u * (uint32_t)__popc(hm & lt);
-                sm_st<0>(at, key[i]);
-                if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+                if (is_hot) at = lead + kSlot * (uint32_t)__popc(hm & lt);
+                if (PAIRS) sm_st2(at, key[i], val[i]);
+                else sm_st<0>(at, key[i]);
             }
         }
     } else {
@@ -296,9 +306,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             if ((peers >> lane) == 1u)  // highest lane of the group
                 base = sm_add_ret(sa_wcnt | d4, (uint32_t)__popc(peers));
             base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
-            const uint32_t at = sa_keys + 4u * (base + (uint32_t)__popc(peers & lt));
-            sm_st<0>(at, key[i]);
-            if (PAIRS) sm_st<TILE * 4>(at, val[i]);
+            const uint32_t at = sa_keys + kSlot * (base + (uint32_t)__popc(peers & lt));
+            if (PAIRS) sm_st2(at, key[i], val[i]);
+            else sm_st<0>(at, key[i]);
         }
     }
 
@@ -347,10 +357,19 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     if (full) {
 #pragma unroll
         for (int k0 = 0; k0 < ITEMS; k0 += kGroup) {
-            uint32_t kk[kGroup], gb[kGroup];
+            uint32_t kk[kGroup], vv[PAIRS ? kGroup : 1], gb[kGroup];
 #pragma unroll
             for (int g = 0; g < kGroup; ++g)
-                if (k0 + g < ITEMS) kk[g] = sm_ld(sa_keys + 4u * (tid + (k0 + g) * THREADS));
+                if (k0 + g < ITEMS) {
+                    const uint32_t j = tid + (k0 + g) * THREADS;
+                    if (PAIRS) {
+                        const uint2 kv = sm_ld2(sa_keys + 8u * j);
+                        kk[g] = kv.x;
+                        vv[g] = kv.y;
+                    } else {
+                        kk[g] = sm_ld(sa_keys + 4u * j);
+                    }
+                }
             if (!DST) {
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
@@ -360,7 +379,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                     if (k0 + g < ITEMS) {
                         const uint32_t j = tid + (k0 + g) * THREADS;
                         kout[gb[g] + j] = kk[g];
-                        if (PAIRS) vout[gb[g] + j] = s_vals[j];
+                        if (PAIRS) vout[gb[g] + j] = vv[g];
                     }
             } else {
 #pragma unroll
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                         const uint64_t off = 4ull * j;
                         *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk[g];
                         if (PAIRS)
-                            *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = s_vals[j];
+                            *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = vv[g];
                     }
             }
         }
@@ -380,17 +399,24 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t j = tid + k * THREADS;
             if (j < n_valid) {
-                const uint32_t kk = s_keys[j];
+                uint32_t kk, vv = 0;
+                if (PAIRS) {
+                    const uint2 kv = sm_ld2(sa_keys + 8u * j);
+                    kk = kv.x;
+                    vv = kv.y;
+                } else {
+                    kk = sm_ld(sa_keys + 4u * j);
+                }
                 const uint32_t d4 = __funnelshift_r(kk, kk, rot) & mask4;
                 if (!DST) {
                     const uint32_t g = sm_ld(sa_gbase | d4) + j;
                     kout[g] = kk;
-                    if (PAIRS) vout[g] = s_vals[j];
+                    if (PAIRS) vout[g] = vv;
                 } else {
                     const uint64_t off = 4ull * j;
                     *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d4 >> 2] + off) = kk;
                     if (PAIRS)
-                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d4 >> 2] + off) = s_vals[j];
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d4 >> 2] + off) = vv;
                 }
             }
         }
