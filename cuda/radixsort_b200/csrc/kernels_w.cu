@@ -20,7 +20,7 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
     constexpr int TB = g.table_bits;
     using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
-    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, PAIRS, DST>;
+    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, PAIRS, DST>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -88,6 +88,11 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 13: return launch_modes<13>(pairs, dst, a, s);
     case 14: return launch_modes<14>(pairs, dst, a, s);
     case 15: return launch_modes<15>(pairs, dst, a, s);
+    case 17: return launch_modes<17>(pairs, dst, a, s);
+    case 18: return launch_modes<18>(pairs, dst, a, s);
+    case 19: return launch_modes<19>(pairs, dst, a, s);
+    case 20: return launch_modes<20>(pairs, dst, a, s);
+    case 21: return launch_modes<21>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -15,26 +15,32 @@ struct PassVariant {
     int min_ctas;
     int mode;
     int table_bits;
+    int lb_batch;  // look-back descriptors in flight per bin thread
 };
-constexpr int kNumVariants = 17;
+constexpr int kNumVariants = 22;
 constexpr PassVariant kVariants[kNumVariants] = {
-    {256, 30, 20, 4, 0, 5},   //  0 default: table(5 bits) + 3 ballots
-    {256, 30, 20, 4, 1, 0},   //  1 atomic rank (selected only after the self test passes)
-    {256, 36, 24, 4, 0, 5},   //  2
-    {256, 36, 20, 4, 1, 0},   //  3
-    {384, 20, 14, 3, 0, 5},   //  4
-    {384, 20, 14, 3, 1, 0},   //  5
-    {256, 30, 20, 4, 0, 8},   //  6 full-digit atomicOr table, no ballots
-    {256, 30, 20, 4, 0, 6},   //  7 table(6 bits) + 2 ballots
-    {384, 20, 14, 2, 2, 0},   //  8 match.any (for the record)
-    {256, 40, 24, 3, 1, 0},   //  9
-    {256, 44, 22, 3, 1, 0},   // 10
-    {512, 36, 24, 2, 1, 0},   // 11
-    {512, 24, 16, 3, 1, 0},   // 12
-    {384, 32, 20, 3, 1, 0},   // 13
-    {384, 24, 16, 3, 1, 0},   // 14
-    {512, 30, 20, 2, 1, 0},   // 15
-    {256, 30, 20, 4, 0, 0},   // 16 ballots only (narrow digits); instantiated for every width
+    {256, 30, 20, 4, 0, 5, 8},   //  0 default: table(5 bits) + 3 ballots
+    {256, 30, 20, 4, 1, 0, 8},   //  1 atomic rank (selected only after the self test passes)
+    {256, 36, 24, 4, 0, 5, 8},   //  2
+    {256, 36, 20, 4, 1, 0, 8},   //  3
+    {384, 20, 14, 3, 0, 5, 8},   //  4
+    {384, 20, 14, 3, 1, 0, 8},   //  5
+    {256, 30, 20, 4, 0, 8, 8},   //  6 full-digit atomicOr table, no ballots
+    {256, 30, 20, 4, 0, 6, 8},   //  7 table(6 bits) + 2 ballots
+    {384, 20, 14, 2, 2, 0, 8},   //  8 match.any (for the record)
+    {256, 40, 24, 3, 1, 0, 8},   //  9
+    {256, 44, 22, 3, 1, 0, 8},   // 10
+    {512, 36, 24, 2, 1, 0, 8},   // 11
+    {512, 24, 16, 3, 1, 0, 8},   // 12
+    {384, 32, 20, 3, 1, 0, 8},   // 13
+    {384, 24, 16, 3, 1, 0, 8},   // 14
+    {512, 30, 20, 2, 1, 0, 8},   // 15
+    {256, 30, 20, 4, 0, 0, 8},   // 16 ballots only (narrow digits); instantiated for every width
+    {256, 44, 22, 3, 1, 0, 4},   // 17 = 10 with a 4-deep look-back
+    {256, 44, 22, 3, 1, 0, 16},  // 18 = 10 with a 16-deep look-back
+    {384, 44, 22, 2, 1, 0, 8},   // 19
+    {512, 22, 12, 3, 1, 0, 8},   // 20
+    {384, 30, 16, 3, 1, 0, 8},   // 21
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

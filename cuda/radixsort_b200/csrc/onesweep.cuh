@@ -115,11 +115,11 @@ struct PassTraits {
     static_assert(TILE % B == 0, "tables must stay aligned to their size");
 };
 
-constexpr int kLookbackBatch = 8;
 constexpr int kGroup = 6;  // shared-memory operations in flight per thread in the rank / write-out loops
 
-template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, bool PAIRS, bool DST>
+template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, int LB, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
+    constexpr int kLookbackBatch = LB;  // descriptors in flight per bin thread during the look-back
     using TR = PassTraits<W, THREADS, ITEMS, MODE, TB, PAIRS, DST>;
     constexpr int B = TR::B;
     constexpr int WARPS = TR::WARPS;
