@@ -93,6 +93,8 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 19: return launch_modes<19>(pairs, dst, a, s);
     case 20: return launch_modes<20>(pairs, dst, a, s);
     case 21: return launch_modes<21>(pairs, dst, a, s);
+    case 22: return launch_modes<22>(pairs, dst, a, s);
+    case 23: return launch_modes<23>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -93,6 +93,14 @@ __device__ __forceinline__ uint2 sm_ld2(uint32_t addr) {
     return r;
 }
 
+// v + (a value that is zero at run time but that neither nvcc nor ptxas can prove to be zero).
+// Used on the rotate amount of each phase: the phases then compute their digit offsets from
+// "different" inputs, so ptxas recomputes them (2 instructions per key) instead of keeping ITEMS
+// of them alive across barriers and branches -- which it does by spilling to local memory, i.e.
+// by adding L1 wavefronts to a kernel that is bound by exactly those.  (A mov-based or empty inline
+// asm is folded away by ptxas and does not help.)
+__device__ __forceinline__ uint32_t launder(uint32_t v, uint32_t runtime_zero) { return v + runtime_zero; }
+
 template <int W, int THREADS, int ITEMS, int MODE, int TB, bool PAIRS, bool DST>
 struct PassTraits {
     static constexpr int B = 1 << W;
@@ -204,8 +212,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         for (int w = 0; w < WARPS; ++w) {
             c[w] = s_cnt[w * B + tid];
             count += c[w];
-            // A digit holding >= 1/4 of a warp's keys makes that warp "skewed": its rank loop
-            // combines the lanes of that digit before the atomic (see step 4).
+            // A digit holding >= 1/4 of a warp's keys marks that warp as clustered: its rank loop
+            // combines runs of equal digits before the atomic (see step 4).
             if (MODE == RANK_ATOMIC && c[w] >= (uint32_t)(WARP_KEYS / 4)) s_hot[w] = (tid << 2) | 1u;
         }
     }
@@ -228,9 +236,23 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     __syncthreads();
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
+    const uint32_t rot_count = rot;  // (documentation only: step 2 used `rot`)
+    (void)rot_count;
     if (MODE == RANK_ATOMIC) {
-        const uint32_t hot = s_hot[warp];
-        if (hot == 0u) {
+        const uint32_t rot = launder(rot_count, a.parity >> 8);  // shadows the outer value for this phase
+        // A warp is "clustered" when lanes of one warp instruction share digits: its hottest digit
+        // holds >= 1/4 of its keys (flag set in step 3), or neighbouring lanes of a sample item
+        // mostly agree (sorted / partially sorted input, data grouped by earlier passes).
+        const uint32_t lt = lanemask_lt();
+        bool clustered = s_hot[warp] != 0u;
+        {
+            const uint32_t d0 = __funnelshift_r(key[0], key[0], rot) & mask4;
+            const uint32_t d1 = __funnelshift_r(key[ITEMS / 2], key[ITEMS / 2], rot) & mask4;
+            const uint32_t h0 = __ballot_sync(0xffffffffu, d0 != __shfl_up_sync(0xffffffffu, d0, 1));
+            const uint32_t h1 = __ballot_sync(0xffffffffu, d1 != __shfl_up_sync(0xffffffffu, d1, 1));
+            clustered = clustered || __popc(h0) <= 16 || __popc(h1) <= 16;
+        }
+        if (!clustered) {
             // Software-pipelined in groups: kGroup atomics in flight before their dependent stores,
             // so a warp pays one shared-memory round trip per group instead of one per key.
 #pragma unroll
@@ -248,26 +270,26 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                     }
             }
         } else {
-            // Skewed warp (sorted / few distinct / heavy-hitter inputs): atom.shared.add with a return
-            // value serialises lanes that share an address (32 cycles per instruction when all 32 do),
-            // so the lanes holding the warp's hot digit are ranked with one ballot and ONE atomic.
-            const uint32_t hot4 = hot & ~3u;
-            const uint32_t lt = lanemask_lt();
+            // atom.shared.add with a return value serialises lanes that share an address (measured:
+            // 32 cycles per instruction when all 32 do), so every RUN of equal digits among
+            // consecutive lanes is ranked by its first lane with ONE atomic of the run length.
+            const uint32_t lanebit = 1u << lane;
+            const uint32_t rot_c = launder(rot_count, a.parity >> 9);  // see launder()
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
-                const uint32_t d4 = __funnelshift_r(key[i], key[i], rot) & mask4;
-                const bool is_hot = d4 == hot4;
-                const uint32_t hm = __ballot_sync(0xffffffffu, is_hot);
+                const uint32_t k = key[i];
+                const uint32_t d4 = __funnelshift_r(k, k, rot_c) & mask4;
+                const uint32_t prev = __shfl_up_sync(0xffffffffu, d4, 1);
+                const bool head = (lane == 0u) || (d4 != prev);
+                const uint32_t hm = __ballot_sync(0xffffffffu, head);        // bit 0 is always set
+                const uint32_t start = 31u - (uint32_t)__clz(hm & (lt | lanebit));  // first lane of my run
+                const uint32_t above = hm & ~(lt | lanebit);                  // run heads above me
+                const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
                 uint32_t at = 0;
-                if (!is_hot) {
-                    at = sm_add_ret(sa_wcnt | d4, kSlot);
-                } else if ((hm & lt) == 0u) {  // lowest hot lane
-                    at = sm_add_ret(sa_wcnt | hot4, kSlot * (uint32_t)__popc(hm));
-                }
-                const uint32_t lead = __shfl_sync(0xffffffffu, at, hm ? (__ffs(hm) - 1) : 0);
-                if (is_hot) at = lead + kSlot * (uint32_t)__popc(hm & lt);
-                if (PAIRS) sm_st2(at, key[i], val[i]);
-                else sm_st<0>(at, key[i]);
+                if (head) at = sm_add_ret(sa_wcnt | d4, kSlot * (end - lane));
+                at = __shfl_sync(0xffffffffu, at, start) + kSlot * (lane - start);
+                if (PAIRS) sm_st2(at, k, val[i]);
+                else sm_st<0>(at, k);
             }
         }
     } else {
