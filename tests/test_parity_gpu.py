@@ -133,6 +133,32 @@ def test_pairs_edge_sizes_and_host_entry(rs, oracle):
         assert np.array_equal(hk, rk) and np.array_equal(hv, rv), n
 
 
+@pytest.mark.parametrize("pattern", ["sorted", "iota", "two_values", "runs_of_16", "lane_period_16", "sawtooth"])
+def test_pairs_stable_on_clustered_keys(rs, oracle, pattern):
+    """Inputs whose equal digits sit in neighbouring lanes (the run-length rank path) or in a
+    fixed lane period (same-address atomics inside one warp instruction): stability must hold."""
+    n = 700001
+    i = np.arange(n, dtype=np.uint64)
+    if pattern == "sorted":
+        k = oracle.generate("sorted", n)
+    elif pattern == "iota":
+        k = oracle.generate("iota", n)
+    elif pattern == "two_values":
+        k = np.where(oracle.generate("uniform", n) & 1, 0xCAFEBABE, 0x12345678).astype(np.uint32)
+    elif pattern == "runs_of_16":
+        k = ((i // 16) * 2654435761 % (1 << 32)).astype(np.uint32)
+    elif pattern == "lane_period_16":
+        k = ((i % 16) * 0x01010101).astype(np.uint32)
+    else:
+        k = ((i % 1000) << 12).astype(np.uint32)
+    v = np.arange(n, dtype=np.uint32)
+    for nbits in (8, 4):
+        ko, vo = rs.sort_pairs(to_dev(k), to_dev(v), nbits)
+        rk, rv = oracle.sort_pairs(k, v, nbits)
+        assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv), (pattern, nbits)
+    assert np.array_equal(dev_sort(rs, k, 8), np.sort(k))
+
+
 def test_pairs_all_equal_keys_is_identity_on_values(rs, oracle):
     n = 100000
     k = oracle.generate("all_equal", n)
