@@ -24,7 +24,7 @@ CLI_PATH = os.path.join(PKG_DIR, "radixsort_cli")
 INCLUDE_DIR = os.path.normpath(os.path.join(PKG_DIR, "..", "..", "include"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE_DIR]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-I", INCLUDE_DIR]
 WIDTHS = range(1, 9)
 
 
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, "b200sort.cu"), "-o", obj])
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
         list(pool.map(lambda c: _run(c, verbose or ptxas_info), jobs))
-    _run([nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs], verbose)
+    _run([nvcc, *ARCH, "-shared", "-Xcompiler", "-pthread", "-o", LIB_PATH, *objs], verbose)
     build_cli(verbose)
     return LIB_PATH
 

@@ -9,8 +9,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/b200sort.h"
@@ -339,11 +341,90 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
 }
 
 // ---- host-pointer wrapper state --------------------------------------------------------------------
+// Pageable host arrays (what the reference's main() passes: plain malloc, SourceCode/Parallel7.cu:
+// 712-715) are moved through a ring of pinned staging buffers: a small pool of host threads copies
+// chunk k+1 into/out of pinned memory while the DMA engine moves chunk k.  Pinned (or registered)
+// arrays are copied directly.
+constexpr size_t kStageChunk = 32u << 20;  // bytes per staging buffer
+constexpr int kStageSlots = 3;
+
+class CopyPool {
+public:
+    void copy(void *dst, const void *src, size_t bytes) {
+        ensure_started();
+        const int parts = (int)workers_.size() + 1;
+        const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = static_cast<char *>(dst);
+            src_ = static_cast<const char *>(src);
+            bytes_ = bytes;
+            per_ = per;
+            pending_ = (int)workers_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        run_part(0);  // the caller takes the first slice
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+
+private:
+    void ensure_started() {
+        if (started_) return;
+        started_ = true;
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = (int)std::min<unsigned>(hw > 2 ? hw / 2 : 1, 6) - 1;
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { worker(i + 1); });
+    }
+    void run_part(int part) {
+        const size_t off = per_ * (size_t)part;
+        if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+    }
+    void worker(int part) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            run_part(part);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --pending_;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    char *dst_ = nullptr;
+    const char *src_ = nullptr;
+    size_t bytes_ = 0, per_ = 0;
+    int pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false, started_ = false;
+};
+
 struct HostCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
-    void *d_buf = nullptr;  // [keys_in | vals_in | keys_out | vals_out | temp]
+    void *d_buf = nullptr;  // [keys_in | keys_out | vals_in | vals_out | temp]
     size_t d_bytes = 0;
+    void *stage[kStageSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr};
+    CopyPool *pool = nullptr;
 } g_host;
 
 int ensure_host_ctx(size_t bytes) {
@@ -358,6 +439,81 @@ int ensure_host_ctx(size_t bytes) {
             return fail(B200SORT_ENOMEM, "cudaMalloc of device staging buffers");
         }
         g_host.d_bytes = bytes;
+    }
+    return 0;
+}
+
+int ensure_staging() {
+    for (int i = 0; i < kStageSlots; ++i) {
+        if (!g_host.stage[i]) {
+            cudaError_t e = cudaMallocHost(&g_host.stage[i], kStageChunk);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(B200SORT_ENOMEM, "cudaMallocHost of pinned staging buffers");
+            }
+        }
+        if (!g_host.stage_ev[i]) CU(cudaEventCreateWithFlags(&g_host.stage_ev[i], cudaEventDisableTiming));
+    }
+    if (!g_host.pool) g_host.pool = new CopyPool();
+    return 0;
+}
+
+bool is_pageable(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// host -> device, asynchronous on g_host.stream as far as the source allows
+int upload(void *d_dst, const void *h_src, size_t bytes) {
+    cudaStream_t s = g_host.stream;
+    if (bytes < (8u << 20) || !is_pageable(h_src)) {
+        CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    int rc = ensure_staging();
+    if (rc) return rc;
+    size_t off = 0;
+    for (int c = 0; off < bytes; ++c, off += kStageChunk) {
+        const int slot = c % kStageSlots;
+        const size_t len = std::min(kStageChunk, bytes - off);
+        CU(cudaEventSynchronize(g_host.stage_ev[slot]));  // the DMA that last used this slot is done
+        g_host.pool->copy(g_host.stage[slot], static_cast<const char *>(h_src) + off, len);
+        CU(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, g_host.stage[slot], len, cudaMemcpyHostToDevice, s));
+        CU(cudaEventRecord(g_host.stage_ev[slot], s));
+    }
+    return 0;
+}
+
+// device -> host; returns after the data is in h_dst when staging is used
+int download(void *h_dst, const void *d_src, size_t bytes) {
+    cudaStream_t s = g_host.stream;
+    if (bytes < (8u << 20) || !is_pageable(h_dst)) {
+        CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+        return 0;
+    }
+    int rc = ensure_staging();
+    if (rc) return rc;
+    const int chunks = (int)((bytes + kStageChunk - 1) / kStageChunk);
+    auto issue = [&](int c) -> cudaError_t {
+        const size_t off = (size_t)c * kStageChunk;
+        const size_t len = std::min(kStageChunk, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(g_host.stage[c % kStageSlots], static_cast<const char *>(d_src) + off, len,
+                                        cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(g_host.stage_ev[c % kStageSlots], s);
+    };
+    for (int c = 0; c < std::min(chunks, kStageSlots - 1); ++c) CU(issue(c));
+    for (int c = 0; c < chunks; ++c) {
+        const int ahead = c + kStageSlots - 1;
+        if (ahead < chunks) CU(issue(ahead));  // its slot was drained by the host copy of chunk c-1
+        const size_t off = (size_t)c * kStageChunk;
+        const size_t len = std::min(kStageChunk, bytes - off);
+        CU(cudaEventSynchronize(g_host.stage_ev[c % kStageSlots]));
+        g_host.pool->copy(static_cast<char *>(h_dst) + off, g_host.stage[c % kStageSlots], len);
     }
     return 0;
 }
@@ -387,12 +543,12 @@ int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
     void *temp = b + arrays * arr;
     cudaStream_t s = g_host.stream;
 
-    CU(cudaMemcpyAsync(dk_in, hk_in, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    if (pairs) CU(cudaMemcpyAsync(dv_in, hv_in, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = upload(dk_in, hk_in, (size_t)n * 4)) != 0) return rc;
+    if (pairs && (rc = upload(dv_in, hv_in, (size_t)n * 4)) != 0) return rc;
     rc = run_sort(dk_in, dv_in, n, dk_out, dv_out, temp, temp_bytes, nbits, s);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(hk_out, dk_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    if (pairs) CU(cudaMemcpyAsync(hv_out, dv_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if ((rc = download(hk_out, dk_out, (size_t)n * 4)) != 0) return rc;
+    if (pairs && (rc = download(hv_out, dv_out, (size_t)n * 4)) != 0) return rc;
     CU(cudaStreamSynchronize(s));
     return B200SORT_OK;
 }
@@ -501,6 +657,14 @@ int b200sort_shutdown(void) {
     if (g_host.d_buf) cudaFree(g_host.d_buf);
     g_host.d_buf = nullptr;
     g_host.d_bytes = 0;
+    for (int i = 0; i < kStageSlots; ++i) {
+        if (g_host.stage[i]) cudaFreeHost(g_host.stage[i]);
+        if (g_host.stage_ev[i]) cudaEventDestroy(g_host.stage_ev[i]);
+        g_host.stage[i] = nullptr;
+        g_host.stage_ev[i] = nullptr;
+    }
+    delete g_host.pool;
+    g_host.pool = nullptr;
     if (g_host.stream) cudaStreamDestroy(g_host.stream);
     g_host.stream = nullptr;
     for (cudaEvent_t ev : g_events) cudaEventDestroy(ev);
