@@ -353,7 +353,7 @@ public:
     void copy(void *dst, const void *src, size_t bytes) {
         ensure_started();
         const int parts = (int)workers_.size() + 1;
-        const size_t per = ((bytes / parts) + 4095) & ~size_t(4095);
+        const size_t per = (((bytes + parts - 1) / parts) + 4095) & ~size_t(4095);  // >= 4096 for bytes > 0
         {
             std::lock_guard<std::mutex> lk(mu_);
             dst_ = static_cast<char *>(dst);

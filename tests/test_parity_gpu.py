@@ -81,6 +81,24 @@ def test_distributions(rs, oracle, kind, nbits):
     assert np.array_equal(dev_sort(rs, k, nbits), oracle.sort_keys(k, nbits))
 
 
+def test_host_entry_staging_chunk_boundaries(rs, oracle):
+    """Pageable host arrays go through 32 MiB pinned staging chunks: sizes around the chunk
+    boundaries, including a last chunk of a single key (the reference's own n = 2^24 + 1)."""
+    chunk = (32 << 20) // 4
+    for n in (2 * chunk - 1, 2 * chunk, 2 * chunk + 1, 3 * chunk + 5, chunk // 4 + 1):
+        k = oracle.generate("uniform", n, first=n)
+        out = np.zeros_like(k)
+        rs.sortByDevice(k, n, out, 8, 512)
+        assert np.array_equal(out, np.sort(k)), n
+    n = 2 * chunk + 1
+    k = oracle.generate("uniform", n) & 0xFFFF
+    v = np.arange(n, dtype=np.uint32)
+    hk, hv = np.zeros_like(k), np.zeros_like(v)
+    rs.sort_pairs_by_device(k, v, n, hk, hv, 8, 512)
+    idx = np.argsort(k, kind="stable")
+    assert np.array_equal(hk, k[idx]) and np.array_equal(hv, v[idx])
+
+
 def test_keys_with_bit31_and_extremes(rs, oracle):
     k = oracle.generate("uniform", 100000)
     k[:5] = [0, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0xFFFFFFFF]
