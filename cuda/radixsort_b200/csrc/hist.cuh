@@ -19,7 +19,8 @@
 namespace b200sort {
 
 // W: log2 of bins per pass.  P_CT > 0: uniform pass list (pass p = bits [p*W, p*W+W)) known at
-// compile time; P_CT == 0: runtime list from args.passes.
+// compile time; P_CT == 0: runtime list from args.passes; P_CT == -1: exactly one runtime digit
+// (args.passes entry 0) -- the multi-GPU top-digit histogram and b200sort_digit_pass.
 template <int W, int P_CT>
 __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a) {
     constexpr int B = 1 << W;
@@ -29,7 +30,8 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a)
     __shared__ uint32_t s_last;
     __shared__ uint32_t s_warp_tot[32];
 
-    const int P = P_CT ? P_CT : a.passes.count;
+    const int P = P_CT > 0 ? P_CT : (P_CT < 0 ? 1 : a.passes.count);
+    const uint32_t shift0 = a.passes.shift[0], mask0 = (1u << a.passes.bits[0]) - 1u;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     {
@@ -47,11 +49,15 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a)
 
     uint32_t *col = s_hist + lane;  // this lane's column
     auto tally = [&](uint32_t key) {
+        if (P_CT < 0) {
+            atomicAdd(col + (((key >> shift0) & mask0) << 5), 1u);
+            return;
+        }
 #pragma unroll
-        for (int p = 0; p < (P_CT ? P_CT : kMaxPasses); ++p) {
-            if (!P_CT && p >= P) break;
-            const uint32_t d = P_CT ? ((key >> (p * W)) & (B - 1))
-                                    : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
+        for (int p = 0; p < (P_CT > 0 ? P_CT : kMaxPasses); ++p) {
+            if (P_CT == 0 && p >= P) break;
+            const uint32_t d = P_CT > 0 ? ((key >> (p * W)) & (B - 1))
+                                        : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
             atomicAdd(col + ((p * B + d) << 5), 1u);
         }
     };

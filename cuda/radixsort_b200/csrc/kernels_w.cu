@@ -21,12 +21,14 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int TB = g.table_bits;
     using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
     auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, PAIRS, DST>;
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;  // one bit per device: the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured >> (dev & 63) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)TR::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     kernel<<<a.num_tiles, g.threads, TR::SMEM_BYTES, s>>>(a);
     return cudaGetLastError();
@@ -47,11 +49,13 @@ template <int P_CT>
 cudaError_t launch_hist_impl(const HistArgs &a, int passes, int grid, cudaStream_t s) {
     auto kernel = hist_kernel<W, P_CT>;
     const size_t smem = hist_smem_bytes(passes, W);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {};  // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     kernel<<<grid, kHistThreads, smem, s>>>(a);
     return cudaGetLastError();
@@ -63,6 +67,7 @@ cudaError_t launch_hist_impl(const HistArgs &a, int passes, int grid, cudaStream
 
 cudaError_t B200_CAT(launch_hist_w, B200_W)(bool uniform, const HistArgs &a, int grid, cudaStream_t s) {
     if (uniform) return launch_hist_impl<P_UNIFORM>(a, P_UNIFORM, grid, s);
+    if (a.passes.count == 1) return launch_hist_impl<-1>(a, 1, grid, s);
     return launch_hist_impl<0>(a, a.passes.count, grid, s);
 }
 

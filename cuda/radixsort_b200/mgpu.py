@@ -108,11 +108,14 @@ class DeviceOps:
     def histogram(self, keys, shift, bits):
         return self.api.histogram(keys, shift, bits, workspace=self.ws)
 
-    def digit_pass(self, keys, shift, bits, out=None, bin_dst=None):
-        return self.api.digit_pass(keys, shift, bits, out_keys=out, bin_dst=bin_dst, workspace=self.ws)
+    def digit_pass(self, keys, shift, bits, out=None, bin_dst=None, vals=None, out_vals=None):
+        return self.api.digit_pass(keys, shift, bits, vals=vals, out_keys=out, out_vals=out_vals,
+                                   bin_dst=bin_dst, workspace=self.ws)
 
-    def sort(self, keys, nbits, out):
-        return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
+    def sort(self, keys, nbits, out, vals=None, out_vals=None):
+        if vals is None:
+            return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
+        return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws)
 
     def empty(self, n):
         return torch.empty(n, dtype=torch.int32, device="cuda")
@@ -140,7 +143,8 @@ class PhaseTimer:
 
 
 class ShardedSorter:
-    """Sorts a uint32 array that is sharded over the ranks of `group` (keys only)."""
+    """Sorts a uint32 array (optionally with uint32 values, stably) that is sharded over the ranks
+    of `group`."""
 
     def __init__(self, group=None, per_rank_capacity: int = 0, nbits: int = 8, fused: bool = False,
                  ops=None, time_phases: bool = True, allow_narrow: bool = True):
@@ -160,6 +164,11 @@ class ShardedSorter:
         self.symm = None
         self.part = None
         self.out = None
+        self.recv_v = None
+        self.peer_ptrs_v = None
+        self.symm_v = None
+        self.part_v = None
+        self.out_v = None
         if self.capacity:
             self._allocate(self.capacity)
 
@@ -178,11 +187,30 @@ class ShardedSorter:
         if not self.fused:
             self.recv = self.ops.empty(capacity)
         self.out = self.ops.empty(capacity)
+        self.recv_v = self.out_v = None      # value buffers are created by the first sort with values
+
+    def _allocate_values(self):
+        if self.recv_v is not None:
+            return
+        if self.fused:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.recv_v = symm_mem.empty(self.capacity, dtype=torch.int32,
+                                         device=torch.device("cuda", torch.cuda.current_device()))
+            self.symm_v = symm_mem.rendezvous(self.recv_v, self.group.group_name)
+            self.peer_ptrs_v = [int(p) for p in self.symm_v.buffer_ptrs]
+        else:
+            self.recv_v = self.ops.empty(self.capacity)
+        self.out_v = self.ops.empty(self.capacity)
 
     # -- the sort -----------------------------------------------------------------------------
-    def sort(self, keys):
+    def sort_pairs(self, keys, vals):
+        """Stable key/value variant: returns (keys, values) slices of the globally sorted pairs."""
+        return self.sort(keys, vals)
+
+    def sort(self, keys, vals=None):
         """keys: this rank's shard (4-byte ints).  Returns this rank's slice of the globally sorted
-        array (a view of an internal buffer, valid until the next call)."""
+        array (a view of an internal buffer, valid until the next call); with `vals`, a pair of
+        slices (equal keys keep their global input order)."""
         ops, world, rank = self.ops, self.world, self.rank
         n_local = keys.numel()
         shift = 32 - TOP_BITS
@@ -203,6 +231,8 @@ class ShardedSorter:
             if self.fused and self.recv is not None:
                 raise RuntimeError(f"receive capacity {self.capacity} < {need}: construct ShardedSorter with a larger per_rank_capacity")
             self._allocate(max(need, int(n_local * 1.05) + 1024))
+        if vals is not None:
+            self._allocate_values()
         t.mark("splitters")
 
         my_total = plan["my_total"]
@@ -214,24 +244,44 @@ class ShardedSorter:
                 addr = np.array([self.peer_ptrs[int(o)] for o in plan["owner"]], dtype=np.int64) + 4 * plan["bin_recv_offset"]
             else:
                 addr = np.array(self.peer_ptrs[:world], dtype=np.int64) + 4 * plan["src_base"]
+            if vals is not None:
+                delta = addr - np.array([self.peer_ptrs[int(o)] for o in plan["owner"]] if pbits == TOP_BITS
+                                        else self.peer_ptrs[:world], dtype=np.int64)
+                vaddr = np.array([self.peer_ptrs_v[int(o)] for o in plan["owner"]] if pbits == TOP_BITS
+                                 else self.peer_ptrs_v[:world], dtype=np.int64) + delta
+                addr = np.concatenate([addr, vaddr])
             bin_dst = torch.from_numpy(addr).to("cuda")
             self.symm.barrier(channel=0)        # peers are done reading their previous receive buffers
-            ops.digit_pass(keys, pshift, pbits, bin_dst=bin_dst)
+            ops.digit_pass(keys, pshift, pbits, bin_dst=bin_dst, vals=vals)
             self.symm.barrier(channel=1)        # every rank's stores have landed
             t.mark("partition+exchange")
         else:
             if self.part is None or self.part.numel() < n_local:
                 self.part = ops.empty(n_local)
-            part = ops.digit_pass(keys, pshift, pbits, out=self.part[:n_local])
+            if vals is None:
+                part = ops.digit_pass(keys, pshift, pbits, out=self.part[:n_local])
+            else:
+                if self.part_v is None or self.part_v.numel() < n_local:
+                    self.part_v = ops.empty(n_local)
+                part, part_v = ops.digit_pass(keys, pshift, pbits, out=self.part[:n_local], vals=vals,
+                                              out_vals=self.part_v[:n_local])
             t.mark("partition")
             self._all_to_all(self.recv[:my_total], part, plan["recv_counts"], plan["send_counts"])
+            if vals is not None:
+                self._all_to_all(self.recv_v[:my_total], part_v, plan["recv_counts"], plan["send_counts"])
             t.mark("exchange")
 
         out = self.out[:my_total]
+        if vals is None:
+            if my_total:
+                ops.sort(self.recv[:my_total], self.nbits, out)
+            t.mark("local_sort")
+            return out
+        out_v = self.out_v[:my_total]
         if my_total:
-            ops.sort(self.recv[:my_total], self.nbits, out)
+            ops.sort(self.recv[:my_total], self.nbits, out, vals=self.recv_v[:my_total], out_vals=out_v)
         t.mark("local_sort")
-        return out
+        return out, out_v
 
     def _all_to_all(self, recv, send, recv_counts, send_counts):
         rc = [int(c) for c in recv_counts]

@@ -80,16 +80,24 @@ class NumpyOps:
         h = np.bincount((k >> shift) & ((1 << bits) - 1), minlength=1 << bits).astype(np.uint32)
         return torch.from_numpy(h.view(np.int32))
 
-    def digit_pass(self, keys, shift, bits, out=None, bin_dst=None):
+    def digit_pass(self, keys, shift, bits, out=None, bin_dst=None, vals=None, out_vals=None):
         k = keys.numpy().view(np.uint32)
         idx = np.argsort((k >> shift) & ((1 << bits) - 1), kind="stable")
         out.numpy().view(np.uint32)[:] = k[idx]
-        return out
+        if vals is None:
+            return out
+        out_vals.numpy()[:] = vals.numpy()[idx]
+        return out, out_vals
 
-    def sort(self, keys, nbits, out):
+    def sort(self, keys, nbits, out, vals=None, out_vals=None):
         import oracle as O
-        out.numpy().view(np.uint32)[:] = O.sort_keys(keys.numpy().view(np.uint32), nbits)
-        return out
+        if vals is None:
+            out.numpy().view(np.uint32)[:] = O.sort_keys(keys.numpy().view(np.uint32), nbits)
+            return out
+        ko, vo = O.sort_pairs(keys.numpy().view(np.uint32), vals.numpy().view(np.uint32), nbits)
+        out.numpy().view(np.uint32)[:] = ko
+        out_vals.numpy().view(np.uint32)[:] = vo
+        return out, out_vals
 
     def empty(self, n):
         return torch.empty(n, dtype=torch.int32)
@@ -121,7 +129,13 @@ def _worker(rank, world, port, kind, n_total, out_dir):
         caught = not mgpu.verify_sharded(broken, keys, verify_fn=_np_verify)
     else:
         caught = not mgpu.verify_sharded(torch.cat([res, res.new_zeros(1)]), keys, verify_fn=_np_verify)
-    np.save(os.path.join(out_dir, f"shard{rank}.npy"), res.numpy().view(np.uint32))
+    np.save(os.path.join(out_dir, f"shard{rank}.npy"), res.numpy().view(np.uint32))   # before buffers are reused
+    # key/value variant: value = global input index, keys with many duplicates
+    kk = torch.from_numpy((keys.numpy().view(np.uint32) & np.uint32(0xFF0000FF)).view(np.int32).copy())
+    vv = torch.arange(first, first + count, dtype=torch.int32)
+    pk, pv = sorter.sort_pairs(kk, vv)
+    np.save(os.path.join(out_dir, f"pairs_k{rank}.npy"), pk.numpy().view(np.uint32).copy())
+    np.save(os.path.join(out_dir, f"pairs_v{rank}.npy"), pv.numpy().view(np.uint32).copy())
     np.save(os.path.join(out_dir, f"flags{rank}.npy"), np.array([ok, caught]))
     dist.destroy_process_group()
 
@@ -146,3 +160,9 @@ def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     assert all(f[1] for f in flags), "verify_sharded accepted a corrupted result"
     if kind == "uniform":
         assert abs(len(shards[0]) - len(shards[1])) < 0.02 * n_total              # balanced split
+    # pairs: concatenation == stable sort of (masked key, global index)
+    pk = np.concatenate([np.load(tmp_path / f"pairs_k{r}.npy") for r in range(world)])
+    pv = np.concatenate([np.load(tmp_path / f"pairs_v{r}.npy") for r in range(world)])
+    mk = whole & np.uint32(0xFF0000FF)
+    rk, rv = O.sort_pairs(mk, np.arange(n_total, dtype=np.uint32), 8)
+    assert np.array_equal(pk, rk) and np.array_equal(pv, rv)

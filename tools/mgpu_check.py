@@ -38,6 +38,18 @@ def main():
             res2 = sorter.sort(keys)                      # buffers are reused correctly
             assert torch.equal(res, res2)
             ok = mgpu.verify_sharded(res, keys)
+            # key/value variant: value = global index; equal keys must keep global input order
+            vals = torch.arange(first, first + count, dtype=torch.int32, device="cuda")
+            res = res.clone()
+            pk, pv = sorter.sort_pairs(keys, vals)
+            assert torch.equal(pk, res), "pair sort disagrees with key sort"
+            same = pk[1:] == pk[:-1]
+            assert bool(torch.all(pv[1:][same] > pv[:-1][same])), "equal keys out of input order"
+            # every (key, value) pair is an input pair: gather the whole input and look the values up
+            full = torch.zeros(total, dtype=torch.int32, device="cuda")
+            full[first:first + count] = keys
+            dist.all_reduce(full)                           # disjoint slices: sum == concatenation
+            ok = ok and bool(torch.equal(full[pv.long()], pk))
             sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
             sizes[rank] = res.numel()
             dist.all_reduce(sizes)
