@@ -43,6 +43,8 @@ SIGNATURES = {
     "b200sort_digit_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
+    "b200sort_scan_temp_bytes": (C.c_size_t, [C.c_uint64]),
+    "b200sort_exclusive_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200sort_generate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
                                     C.c_void_p, C.c_void_p]),
     "b200sort_verify": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -28,7 +28,7 @@ from ._lib import RadixSortError
 __all__ = [
     "Implementation", "SORT_BY_HOST", "SORT_BY_THRUST", "SORT_BY_DEVICE", "sort", "sortByDevice",
     "sort_by_device", "sort_pairs_by_device", "Workspace", "sort_keys", "sort_pairs", "histogram",
-    "digit_pass", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
+    "digit_pass", "exclusive_scan", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
     "tile_keys", "set_param", "get_param", "profile_enable", "profile_read", "launch_count",
     "shutdown",
 ]
@@ -240,6 +240,19 @@ def digit_pass(keys, shift: int, bits: int, vals=None, out_keys=None, out_vals=N
                                        n, okp, ovp, shift, bits, dstp, tmp.data_ptr(), tmp.numel(),
                                        _stream_ptr(stream)))
     return (out_keys, out_vals) if vals is not None else out_keys
+
+
+def exclusive_scan(x, out=None, workspace: Workspace | None = None, stream=None):
+    """Device-wide exclusive prefix sum of a 4-byte integer tensor (mod 2^32): b200sort_exclusive_scan."""
+    torch = _torch()
+    n = x.numel()
+    out = torch.empty_like(x) if out is None else out
+    ws = workspace or _workspace(x.device)
+    lib = _lib.load()
+    tmp = ws.get(int(lib.b200sort_scan_temp_bytes(n)))
+    _lib.check(lib.b200sort_exclusive_scan(_dev_ptr(x, "x"), n, _dev_ptr(out, "out"), tmp.data_ptr(), tmp.numel(),
+                                           _stream_ptr(stream)))
+    return out
 
 
 _zipf_cdf_dev: dict = {}

@@ -17,6 +17,7 @@
 
 #include "../../../include/b200sort.h"
 #include "launch.h"
+#include "scan.cuh"
 #include "util_kernels.cuh"
 
 namespace b200sort {
@@ -769,6 +770,29 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
         a.parity = 0;
         CU(launch_pass(bits, variant, pairs, dst, a, s));
     }
+    return 0;
+}
+
+size_t b200sort_scan_temp_bytes(uint64_t n) {
+    return align_up(((n + kScanTile - 1) / kScanTile) * sizeof(uint64_t), 256) + 256;
+}
+
+int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp, size_t temp_bytes,
+                            void *stream) {
+    if (n == 0) return 0;
+    if (!d_in || !d_out) return fail(B200SORT_EINVAL, "null buffer");
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15u) return fail(B200SORT_EINVAL, "scan buffers must be 16-byte aligned");
+    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles > 0x7FFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < b200sort_scan_temp_bytes(n))
+        return fail(B200SORT_ETEMP, "temp storage");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(d_temp, 0, tiles * sizeof(uint64_t), s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    exclusive_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(d_in, d_out, n, static_cast<uint64_t *>(d_temp));
+    CU(cudaGetLastError());
     return 0;
 }
 

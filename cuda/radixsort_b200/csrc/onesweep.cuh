@@ -164,8 +164,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
-    // byte offset of a key's digit inside a 4-byte-entry table: (rotr(key, shift-2) & mask4)
+    // byte offset of a key's digit inside a 4-byte-entry table: (rotr(key, shift-2) & mask4).
+    // Every phase uses its own laundered copy of the rotate amount (see launder()).
     const uint32_t rot = (a.shift + 30u) & 31u;
+    const uint32_t rot_fast = launder(rot, a.parity >> 8);
+    const uint32_t rot_clustered = launder(rot, a.parity >> 9);
     const uint32_t mask4 = a.mask << 2;
 
     // ---- 1. load ----------------------------------------------------------------------------
@@ -236,18 +239,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     __syncthreads();
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
-    const uint32_t rot_count = rot;  // (documentation only: step 2 used `rot`)
-    (void)rot_count;
     if (MODE == RANK_ATOMIC) {
-        const uint32_t rot = launder(rot_count, a.parity >> 8);  // shadows the outer value for this phase
         // A warp is "clustered" when lanes of one warp instruction share digits: its hottest digit
         // holds >= 1/4 of its keys (flag set in step 3), or neighbouring lanes of a sample item
         // mostly agree (sorted / partially sorted input, data grouped by earlier passes).
         const uint32_t lt = lanemask_lt();
         bool clustered = s_hot[warp] != 0u;
         {
-            const uint32_t d0 = __funnelshift_r(key[0], key[0], rot) & mask4;
-            const uint32_t d1 = __funnelshift_r(key[ITEMS / 2], key[ITEMS / 2], rot) & mask4;
+            const uint32_t d0 = __funnelshift_r(key[0], key[0], rot_fast) & mask4;
+            const uint32_t d1 = __funnelshift_r(key[ITEMS / 2], key[ITEMS / 2], rot_fast) & mask4;
             const uint32_t h0 = __ballot_sync(0xffffffffu, d0 != __shfl_up_sync(0xffffffffu, d0, 1));
             const uint32_t h1 = __ballot_sync(0xffffffffu, d1 != __shfl_up_sync(0xffffffffu, d1, 1));
             clustered = clustered || __popc(h0) <= 16 || __popc(h1) <= 16;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
                     if (i0 + g < ITEMS)
-                        at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot) & mask4), kSlot);
+                        at[g] = sm_add_ret(sa_wcnt | (__funnelshift_r(key[i0 + g], key[i0 + g], rot_fast) & mask4), kSlot);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
                     if (i0 + g < ITEMS) {
@@ -274,11 +274,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             // 32 cycles per instruction when all 32 do), so every RUN of equal digits among
             // consecutive lanes is ranked by its first lane with ONE atomic of the run length.
             const uint32_t lanebit = 1u << lane;
-            const uint32_t rot_c = launder(rot_count, a.parity >> 9);  // see launder()
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t k = key[i];
-                const uint32_t d4 = __funnelshift_r(k, k, rot_c) & mask4;
+                const uint32_t d4 = __funnelshift_r(k, k, rot_clustered) & mask4;
                 const uint32_t prev = __shfl_up_sync(0xffffffffu, d4, 1);
                 const bool head = (lane == 0u) || (d4 != prev);
                 const uint32_t hm = __ballot_sync(0xffffffffu, head);        // bit 0 is always set
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         const uint32_t sa_wmask = smem_u32(smem + TR::OFF_MASK + warp * 2 * TABLE);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t d4 = __funnelshift_r(key[i], key[i], rot) & mask4;
+            const uint32_t d4 = __funnelshift_r(key[i], key[i], rot_fast) & mask4;
             uint32_t peers;
             if (MODE == RANK_MATCH) {
                 peers = __match_any_sync(0xffffffffu, d4);

@@ -1,0 +1,109 @@
+// scan.cuh -- device-wide exclusive prefix sum of uint32 (mod 2^32) in ONE pass with a decoupled
+// look-back: the public form of the reference's scan stage -- scan() + scanBlocks +
+// addScannedBlockSumsToScannedBlocks (SourceCode/Parallel7.cu:408-528), which scans 2*blockSize
+// elements per block with a Blelloch tree, copies the block totals to the HOST, scans them there
+// and launches a second kernel to add them back -- and of the standalone study
+// Docs/Snippets/PrefixSum-WorkEfficient.cu.  8 bytes of HBM traffic per element, no host round trip.
+#pragma once
+#include "common.cuh"
+
+namespace b200sort {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanVecs = 4;                                  // uint4 per thread
+constexpr int kScanTile = kScanThreads * kScanVecs * 4;       // 4096 elements per tile
+
+// descriptor: {status in the high word | value in the low word}; 0 = not ready
+constexpr uint64_t kScanAggregate = 1ull << 32;
+constexpr uint64_t kScanInclusive = 2ull << 32;
+
+__device__ __forceinline__ uint64_t ld_relaxed_gpu64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu64(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// desc: one zeroed uint64 per tile.  Requires in/out 16-byte aligned (checked by the host); the
+// ragged tail (n % 4 elements and the last partial tile) is handled with scalar accesses.
+__global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t *in, uint32_t *out, uint64_t n,
+                                                                       uint64_t *desc) {
+    __shared__ uint32_t s_warp_tot[32];
+    __shared__ uint32_t s_prefix;
+    __shared__ uint32_t s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint64_t tile = blockIdx.x;
+    const uint64_t base = tile * kScanTile;
+    const bool full = base + kScanTile <= n;
+
+    // thread t owns kScanVecs*4 consecutive elements: coalescing comes from the 16-byte vectors
+    uint32_t v[kScanVecs * 4];
+    const uint64_t first = base + (uint64_t)tid * (kScanVecs * 4);
+    if (full) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + first);
+#pragma unroll
+        for (int q = 0; q < kScanVecs; ++q) {
+            const uint4 x = ld_stream_v4(src + q);
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kScanVecs * 4; ++e) v[e] = (first + e < n) ? in[first + e] : 0u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int e = 0; e < kScanVecs * 4; ++e) {
+        const uint32_t x = v[e];
+        v[e] = sum;  // exclusive within the thread
+        sum += x;
+    }
+    const uint32_t thread_excl = block_exclusive_scan<kScanThreads>(sum, s_warp_tot);
+    // tile total = exclusive prefix of the last thread + its sum
+    if (tid == kScanThreads - 1) {
+        const uint32_t total = thread_excl + sum;
+        st_relaxed_gpu64(desc + tile, (tile == 0 ? kScanInclusive : kScanAggregate) | total);
+        s_total = total;
+    }
+    __syncthreads();
+    // look-back by warp 0: 32 predecessors per step
+    if (tid < 32) {
+        uint32_t excl = 0;
+        if (tile != 0) {
+            int64_t t = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t mine = t - (int64_t)lane;
+                uint64_t d = kScanInclusive;  // before tile 0: an inclusive prefix of zero
+                if (mine >= 0) {
+                    do {
+                        d = ld_relaxed_gpu64(desc + mine);
+                    } while ((d >> 32) == 0);
+                }
+                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d >> 32) == 2u);
+                // lanes up to and including the nearest inclusive descriptor contribute
+                const uint32_t upto = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 31u;
+                const uint32_t part = (lane <= upto) ? (uint32_t)d : 0u;
+                excl += __reduce_add_sync(0xffffffffu, part);
+                if (incl_mask) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_gpu64(desc + tile, kScanInclusive | (uint32_t)(excl + s_total));
+        }
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    const uint32_t offset = s_prefix + thread_excl;
+    if (full) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out + first);
+#pragma unroll
+        for (int q = 0; q < kScanVecs; ++q)
+            dst[q] = make_uint4(v[4 * q] + offset, v[4 * q + 1] + offset, v[4 * q + 2] + offset, v[4 * q + 3] + offset);
+    } else {
+#pragma unroll
+        for (int e = 0; e < kScanVecs * 4; ++e)
+            if (first + e < n) out[first + e] = v[e] + offset;
+    }
+}
+
+}  // namespace b200sort

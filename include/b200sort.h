@@ -106,6 +106,15 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
                         const uint64_t *d_bin_dst, void *d_temp, size_t temp_bytes,
                         void *stream);
 
+/* Device-wide exclusive prefix sum of uint32 (mod 2^32), one pass, decoupled look-back.  The
+ * public form of the reference's scan stage: scan() + scanBlocks + addScannedBlockSumsToScannedBlocks
+ * with its host round trip (SourceCode/Parallel7.cu:408-528), and of Docs/Snippets/
+ * PrefixSum-WorkEfficient.cu.  d_in / d_out 16-byte aligned; d_out may equal d_in.
+ * Temp: b200sort_scan_temp_bytes(n), 256-byte aligned. */
+size_t b200sort_scan_temp_bytes(uint64_t n);
+int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp,
+                            size_t temp_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Measurement and test utilities (device side of SURVEY.md section 8d's workloads).
  */

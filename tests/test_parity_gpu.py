@@ -289,6 +289,28 @@ def test_digit_pass_with_per_bin_destinations(rs, oracle):
         assert int(kbufs[b][-1]) == 0       # nothing written past the bin
 
 
+def test_exclusive_scan_matches_the_reference_scan_semantics(rs, oracle):
+    """b200sort_exclusive_scan == the exclusive scan of the reference's scan() stage
+    (SourceCode/Parallel7.cu:485-528; sequential form SourceCode/Baseline1.cu:39-42), mod 2^32."""
+    import torch
+    for n in (1, 2, 31, 4095, 4096, 4097, 8191, 100003, (1 << 24) + 1):
+        x = oracle.generate("uniform", n, first=n) >> 8        # sums wrap modulo 2^32 for the large n
+        ref = np.concatenate([[0], np.cumsum(x[:-1], dtype=np.uint64)]).astype(np.uint64) & 0xFFFFFFFF
+        got = to_host(rs.exclusive_scan(to_dev(x)))
+        assert np.array_equal(got, ref.astype(np.uint32)), n
+    # the tile x bin table of a digit pass, bin-major, scanned: Baseline4.cu:127-138
+    k = oracle.generate("uniform", 50000)
+    table, scan = oracle.tile_table(k, 1024, 8, 4)
+    flat = np.ascontiguousarray(table.T).reshape(-1)
+    got = to_host(rs.exclusive_scan(to_dev(flat))).reshape(16, -1).T
+    assert np.array_equal(got, scan)
+    # in place
+    d = to_dev(np.ones(70001, np.uint32))
+    rs.exclusive_scan(d, out=d)
+    assert np.array_equal(to_host(d), np.arange(70001, dtype=np.uint32))
+    torch.cuda.synchronize()
+
+
 def test_device_generators_match_the_oracle(rs, oracle):
     n = 100003
     for kind in oracle.GEN_KINDS:
