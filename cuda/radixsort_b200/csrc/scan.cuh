@@ -27,7 +27,7 @@ __device__ __forceinline__ void st_relaxed_gpu64(uint64_t *p, uint64_t v) {
 }
 
 // desc: one zeroed uint64 per tile.  Requires in/out 16-byte aligned (checked by the host); the
-// ragged tail (n % 4 elements and the last partial tile) is handled with scalar accesses.
+// last partial tile is handled with scalar accesses.
 __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t *in, uint32_t *out, uint64_t n,
                                                                        uint64_t *desc) {
     __shared__ uint32_t s_warp_tot[32];
@@ -38,30 +38,54 @@ __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint
     const uint64_t base = tile * kScanTile;
     const bool full = base + kScanTile <= n;
 
-    // thread t owns kScanVecs*4 consecutive elements: coalescing comes from the 16-byte vectors
+    // Warp w owns kScanVecs*128 consecutive elements and reads them in kScanVecs rounds of one
+    // fully coalesced 512-byte request: lane l of round q holds elements [(w*kScanVecs+q)*128 + 4l, +4).
+    const uint32_t warp = tid >> 5;
     uint32_t v[kScanVecs * 4];
-    const uint64_t first = base + (uint64_t)tid * (kScanVecs * 4);
+    const uint64_t wbase = base + (uint64_t)warp * (kScanVecs * 128);
     if (full) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(in + first);
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + wbase) + lane;
 #pragma unroll
         for (int q = 0; q < kScanVecs; ++q) {
-            const uint4 x = ld_stream_v4(src + q);
+            const uint4 x = ld_stream_v4(src + q * 32);
             v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < kScanVecs * 4; ++e) v[e] = (first + e < n) ? in[first + e] : 0u;
-    }
-    uint32_t sum = 0;
+        for (int q = 0; q < kScanVecs; ++q)
 #pragma unroll
-    for (int e = 0; e < kScanVecs * 4; ++e) {
-        const uint32_t x = v[e];
-        v[e] = sum;  // exclusive within the thread
-        sum += x;
+            for (int e = 0; e < 4; ++e) {
+                const uint64_t i = wbase + (uint64_t)q * 128 + lane * 4 + e;
+                v[4 * q + e] = (i < n) ? in[i] : 0u;
+            }
     }
-    const uint32_t thread_excl = block_exclusive_scan<kScanThreads>(sum, s_warp_tot);
-    // tile total = exclusive prefix of the last thread + its sum
-    if (tid == kScanThreads - 1) {
+    // exclusive scan inside the warp's slice: within the vector, across lanes, across rounds
+    uint32_t sum = 0;  // becomes the warp total (uniform across the warp)
+#pragma unroll
+    for (int q = 0; q < kScanVecs; ++q) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t x = v[4 * q + e];
+            v[4 * q + e] = t;
+            t += x;
+        }
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const uint32_t lane_excl = sum + incl - t;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[4 * q + e] += lane_excl;
+        sum += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    // block scan over the warp totals (one value per warp, carried by lane 0)
+    const uint32_t warp_excl_all = block_exclusive_scan<kScanThreads>(lane == 0 ? sum : 0u, s_warp_tot);
+    const uint32_t thread_excl = __shfl_sync(0xffffffffu, warp_excl_all, 0);
+    // tile total = exclusive prefix of the last warp + its total
+    if (tid == kScanThreads - 32) {
         const uint32_t total = thread_excl + sum;
         st_relaxed_gpu64(desc + tile, (tile == 0 ? kScanInclusive : kScanAggregate) | total);
         s_total = total;
@@ -95,14 +119,18 @@ __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint
     __syncthreads();
     const uint32_t offset = s_prefix + thread_excl;
     if (full) {
-        uint4 *dst = reinterpret_cast<uint4 *>(out + first);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + wbase) + lane;
 #pragma unroll
         for (int q = 0; q < kScanVecs; ++q)
-            dst[q] = make_uint4(v[4 * q] + offset, v[4 * q + 1] + offset, v[4 * q + 2] + offset, v[4 * q + 3] + offset);
+            dst[q * 32] = make_uint4(v[4 * q] + offset, v[4 * q + 1] + offset, v[4 * q + 2] + offset, v[4 * q + 3] + offset);
     } else {
 #pragma unroll
-        for (int e = 0; e < kScanVecs * 4; ++e)
-            if (first + e < n) out[first + e] = v[e] + offset;
+        for (int q = 0; q < kScanVecs; ++q)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint64_t i = wbase + (uint64_t)q * 128 + lane * 4 + e;
+                if (i < n) out[i] = v[4 * q + e] + offset;
+            }
     }
 }
 
