@@ -50,7 +50,7 @@ def main():
     p = rs.digit_pass(dev(k), 29, 3)
     assert np.array_equal(host(p), k[np.argsort(k >> 29, kind="stable")])
     x = (k >> 12)
-    ref = np.concatenate([[0], np.cumsum(x[:-1], dtype=np.uint64)]) & 0xFFFFFFFF
+    ref = np.concatenate([np.zeros(1, np.uint64), np.cumsum(x[:-1], dtype=np.uint64)]) & np.uint64(0xFFFFFFFF)
     assert np.array_equal(host(rs.exclusive_scan(dev(x))), ref.astype(np.uint32))
     out = np.zeros_like(k)
     rs.sortByDevice(k, k.size, out, 8, 512)
