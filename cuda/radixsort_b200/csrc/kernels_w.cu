@@ -100,6 +100,10 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 21: return launch_modes<21>(pairs, dst, a, s);
     case 22: return launch_modes<22>(pairs, dst, a, s);
     case 23: return launch_modes<23>(pairs, dst, a, s);
+    case 24: return launch_modes<24>(pairs, dst, a, s);
+    case 25: return launch_modes<25>(pairs, dst, a, s);
+    case 26: return launch_modes<26>(pairs, dst, a, s);
+    case 27: return launch_modes<27>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -17,7 +17,7 @@ struct PassVariant {
     int table_bits;
     int lb_batch;  // look-back descriptors in flight per bin thread
 };
-constexpr int kNumVariants = 24;
+constexpr int kNumVariants = 28;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8},   //  1 atomic rank (selected only after the self test passes)
@@ -43,6 +43,10 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {384, 30, 16, 3, 1, 0, 8},   // 21
     {256, 44, 22, 4, 1, 0, 8},   // 22 = 10 at four CTAs per SM
     {256, 40, 20, 4, 1, 0, 8},   // 23
+    {256, 52, 26, 3, 1, 0, 8},   // 24
+    {256, 60, 30, 3, 1, 0, 8},   // 25
+    {256, 64, 32, 2, 1, 0, 8},   // 26
+    {256, 48, 24, 3, 1, 0, 8},   // 27
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
