@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200sort_exclusive_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200sort_generate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64,
                                     C.c_void_p, C.c_void_p]),
+    "b200sort_store_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
     "b200sort_verify": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200sort_profile_enable": (C.c_int, [C.c_int]),
     "b200sort_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),

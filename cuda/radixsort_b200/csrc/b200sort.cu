@@ -811,6 +811,16 @@ int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind,
     return 0;
 }
 
+int b200sort_store_probe(uint32_t *d_dst, const uint32_t *d_src, uint64_t n, int vec, int ctas_per_sm, void *stream) {
+    if (!d_dst || !d_src || (vec != 1 && vec != 4) || ctas_per_sm < 1) return fail(B200SORT_EINVAL, "store probe arguments");
+    int rc = check_device();
+    if (rc) return rc;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    store_probe_kernel<<<g_num_sms * ctas_per_sm, 256, 0, (cudaStream_t)stream>>>(d_dst, d_src, n, vec);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void *stream) {
     if (!d_result || (n > 0 && !d_keys)) return fail(B200SORT_EINVAL, "null buffer");
     int rc = check_device();

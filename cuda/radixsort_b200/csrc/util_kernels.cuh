@@ -77,4 +77,19 @@ __global__ void __launch_bounds__(256) verify_kernel(const uint32_t *__restrict_
     }
 }
 
+// Probe for the fused exchange: copies n uint32 from src to dst (dst may be peer memory) with
+// 4-byte (vec = 1) or 16-byte (vec = 4) stores per lane, `chunk` consecutive keys per warp visit
+// (chunk = 32 imitates the digit-pass write-out: one 128-byte run per warp store).
+__global__ void __launch_bounds__(256) store_probe_kernel(uint32_t *dst, const uint32_t *__restrict__ src, uint64_t n,
+                                                          int vec) {
+    if (vec == 4) {
+        const uint64_t n4 = n >> 2;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
 }  // namespace b200sort

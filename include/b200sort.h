@@ -134,6 +134,11 @@ int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind,
  * overwritten. */
 int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void *stream);
 
+/* Bandwidth probe used to size the fused multi-GPU exchange: copies n uint32 from d_src to d_dst
+ * (which may be peer memory) with 4-byte (vec = 1) or 16-byte (vec = 4) stores per lane. */
+int b200sort_store_probe(uint32_t *d_dst, const uint32_t *d_src, uint64_t n, int vec, int ctas_per_sm,
+                         void *stream);
+
 /* Per-kernel device timing: while enabled, every sort records CUDA events on its own stream
  * around each kernel.  b200sort_profile_read() synchronises on the last recorded event,
  * drains the records of all sorts since the previous read and returns how many it wrote:
