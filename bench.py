@@ -388,6 +388,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-narrow", action="store_true")
+    ap.add_argument("--narrow-variant", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -396,6 +397,9 @@ def main():
     if args.variant is not None:
         import cuda.radixsort_b200 as rs
         rs.set_param("variant", args.variant)
+    if args.narrow_variant is not None:
+        import cuda.radixsort_b200 as rs
+        rs.set_param("narrow_variant", args.narrow_variant)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 or args.gpus > 1:
         if world == 1:

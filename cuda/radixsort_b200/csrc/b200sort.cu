@@ -30,6 +30,7 @@ struct Params {
     int variant = -1;  // -1 = automatic choice (see effective_variant)
     int portion_tiles = 0;  // 0 = as many as fit the 30-bit descriptor value
     int hist_ctas_per_sm = 2;
+    int narrow_variant = -1;  // digit passes of <= 3 bits: -1 = kBallotVariant
 } g_params;
 
 // RANK_ATOMIC variants are only used after the on-device self test has passed.
@@ -109,8 +110,8 @@ struct Layout {
     uint64_t total_tiles;
     uint64_t portion_tiles;  // tiles per launch
     uint64_t portions;
-    // zeroed header: tickets[passes * portions] | done | zeros[bins] | ghist[passes * bins]
-    size_t off_tickets, off_done, off_zeros, off_ghist, header_bytes;
+    // zeroed header: done | zeros[bins] | ghist[passes * bins]
+    size_t off_done, off_zeros, off_ghist, header_bytes;
     size_t off_bin_base;  // [passes][2][bins]
     size_t off_desc;      // [total_tiles][bins]
     size_t desc_bytes;
@@ -131,8 +132,6 @@ Layout make_layout(uint64_t n, int passes, int width, bool pairs, bool need_alt,
     L.portion_tiles = std::max<uint64_t>(1, std::min<uint64_t>(cap, std::max<uint64_t>(L.total_tiles, 1)));
     L.portions = std::max<uint64_t>(1, (L.total_tiles + L.portion_tiles - 1) / L.portion_tiles);
     size_t off = 0;
-    L.off_tickets = off;  off += (size_t)passes * L.portions * 4;
-    off = align_up(off, 16);
     L.off_done = off;     off += 16;
     L.off_zeros = off;    off += (size_t)L.bins * 4;
     L.off_ghist = off;    off += (size_t)passes * L.bins * 4;
@@ -174,7 +173,9 @@ constexpr int kAutoVariantW8 = 10;
 
 int effective_variant(int width) {
     int v = g_params.variant;
-    if (v < 0) v = (width == 8) ? kAutoVariantW8 : (width <= 3 ? kBallotVariant : 1);
+    if (v < 0)
+        v = (width == 8) ? kAutoVariantW8
+                         : (width <= 3 ? (g_params.narrow_variant >= 0 ? g_params.narrow_variant : kBallotVariant) : 1);
     if (!variant_available(width, v)) v = 0;
     if (variant_mode(v) == 1 && !run_selftest()) {
         // same geometry, table rank: variants are laid out as (table, atomic) twins where possible
@@ -185,18 +186,12 @@ int effective_variant(int width) {
 }
 
 // Upper bound of the temp storage a sort / digit pass can need, independent of the tuning
-// parameters in effect (descriptors sized for the smallest tile, one ticket per pass and
-// per minimal portion).
+// parameters in effect (descriptors sized for the smallest tile).
 size_t temp_upper_bound(uint64_t n, int nbits, bool pairs) {
     PassList pl;
     if (!build_pass_list(nbits, pl)) return 0;
     Layout L = make_layout(n, pl.count, pl.width, pairs, true, kMinTileKeys, 0);
-    size_t extra_tickets = 0;
-    if (g_params.portion_tiles > 0) {
-        const uint64_t tiles = (n + kMinTileKeys - 1) / kMinTileKeys;
-        extra_tickets = align_up((size_t)pl.count * ((tiles / g_params.portion_tiles) + 2) * 4, 256);
-    }
-    return L.total + extra_tickets + 4096;
+    return L.total + 4096;
 }
 
 // ---- profiling events --------------------------------------------------------------------------
@@ -286,7 +281,6 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
     if (temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage too small");
 
     char *base = static_cast<char *>(temp);
-    uint32_t *tickets = reinterpret_cast<uint32_t *>(base + L.off_tickets);
     uint32_t *done = reinterpret_cast<uint32_t *>(base + L.off_done);
     uint32_t *ghist = reinterpret_cast<uint32_t *>(base + L.off_ghist);
     uint32_t *bin_base = reinterpret_cast<uint32_t *>(base + L.off_bin_base);
@@ -327,7 +321,6 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
             a.bin_base = bin_base + ((size_t)(2 * p) + (q & 1)) * L.bins;
             a.carry_out = (q + 1 < L.portions) ? bin_base + ((size_t)(2 * p) + ((q + 1) & 1)) * L.bins : nullptr;
             a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
-            a.ticket = tickets + (size_t)p * L.portions + q;
             a.bin_dst = nullptr;
             a.n = (uint32_t)count;
             a.num_tiles = (uint32_t)((count + tile - 1) / tile);
@@ -612,6 +605,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.portion_tiles = value;
         return 0;
     }
+    if (!strcmp(name, "narrow_variant")) {
+        if (value != -1 && value != kBallotVariant && value != kBallotSmallVariant) return B200SORT_EINVAL;
+        g_params.narrow_variant = value;
+        return 0;
+    }
     if (!strcmp(name, "hist_ctas_per_sm")) {
         if (value < 1 || value > 4) return B200SORT_EINVAL;
         g_params.hist_ctas_per_sm = value;
@@ -720,12 +718,12 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     cudaStream_t s = (cudaStream_t)stream;
 
     int variant = effective_variant(bits);
-    if (dst && variant > 1 && variant != kBallotVariant) variant = variant_mode(variant) == 1 ? 1 : 0;
+    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant)
+        variant = variant_mode(variant) == 1 ? 1 : 0;
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);
     if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage");
     char *base = static_cast<char *>(d_temp);
-    uint32_t *tickets = reinterpret_cast<uint32_t *>(base + L.off_tickets);
     uint32_t *bin_base = reinterpret_cast<uint32_t *>(base + L.off_bin_base);
     uint32_t *desc = reinterpret_cast<uint32_t *>(base + L.off_desc);
 
@@ -761,7 +759,6 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
         a.bin_base = bin_base + (q & 1) * L.bins;
         a.carry_out = (q + 1 < L.portions) ? bin_base + ((q + 1) & 1) * L.bins : nullptr;
         a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
-        a.ticket = tickets + q;
         a.bin_dst = d_bin_dst;
         a.n = (uint32_t)count;
         a.num_tiles = (uint32_t)((count + tile - 1) / tile);

@@ -38,7 +38,7 @@ template <int V>
 cudaError_t launch_modes(bool pairs, bool dst, const PassArgs &a, cudaStream_t s) {
     if (!pairs && !dst) return launch_variant<V, false, false>(a, s);
     if (pairs && !dst) return launch_variant<V, true, false>(a, s);
-    if constexpr (V <= 1 || V == kBallotVariant) {
+    if constexpr (V <= 1 || V == kBallotVariant || V == kBallotSmallVariant) {
         if (!pairs && dst) return launch_variant<V, false, true>(a, s);
         return launch_variant<V, true, true>(a, s);
     }
@@ -73,11 +73,12 @@ cudaError_t B200_CAT(launch_hist_w, B200_W)(bool uniform, const HistArgs &a, int
 
 cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, const PassArgs &a,
                                             cudaStream_t s) {
-    if (dst && variant > 1 && variant != kBallotVariant) variant = 0;
+    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant) variant = 0;
     switch (variant) {
     case 0: return launch_modes<0>(pairs, dst, a, s);
     case 1: return launch_modes<1>(pairs, dst, a, s);
     case kBallotVariant: return launch_modes<kBallotVariant>(pairs, dst, a, s);
+    case kBallotSmallVariant: return launch_modes<kBallotSmallVariant>(pairs, dst, a, s);
 #if B200_W == 8
     case 2: return launch_modes<2>(pairs, dst, a, s);
     case 3: return launch_modes<3>(pairs, dst, a, s);

@@ -17,7 +17,7 @@ struct PassVariant {
     int table_bits;
     int lb_batch;  // look-back descriptors in flight per bin thread
 };
-constexpr int kNumVariants = 28;
+constexpr int kNumVariants = 29;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8},   //  1 atomic rank (selected only after the self test passes)
@@ -47,6 +47,7 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 60, 30, 3, 1, 0, 8},   // 25
     {256, 64, 32, 2, 1, 0, 8},   // 26
     {256, 48, 24, 3, 1, 0, 8},   // 27
+    {256, 16, 12, 6, 0, 0, 8},   // 28 ballots only, small tile / high occupancy (fused exchange experiments)
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
@@ -59,8 +60,9 @@ constexpr int kMinTileKeys = 2048;
 // true if (width, variant) is instantiated; callers fall back to variant 0 otherwise.
 // Every width also carries variant 1 (same geometry as 0, atomic rank).
 constexpr int kBallotVariant = 16;
+constexpr int kBallotSmallVariant = 28;
 inline bool variant_available(int width, int variant) {
-    return variant == 0 || variant == 1 || variant == kBallotVariant ||
+    return variant == 0 || variant == 1 || variant == kBallotVariant || variant == kBallotSmallVariant ||
            (width == 8 && variant > 0 && variant < kNumVariants);
 }
 
