@@ -105,7 +105,9 @@ __device__ __forceinline__ uint32_t launder(uint32_t v, uint32_t runtime_zero) {
 // XOR-folded into its low nibble.  The fold is a bijection on [0, 2^W) and spreads digit values
 // that differ only in their high bits -- keys that are multiples of 16, sorted input -- over all
 // 32 shared-memory banks instead of two (measured: 1.43 ms -> see profiles for a sorted pass 0).
-// Uniform digits are unaffected.  Every table indexed by digit uses the folded index.
+// Uniform digits are unaffected.  Used for the per-warp counter tables (count and rank phases);
+// the write-out's base table is read by runs of lanes with the same digit (broadcast), so it
+// keeps the plain index.
 __device__ __forceinline__ uint32_t digit_slot(uint32_t key, uint32_t rot, uint32_t mask4) {
     const uint32_t r = __funnelshift_r(key, key, rot) & mask4;
     return r ^ ((r >> 4) & 0x3Cu);
@@ -374,11 +376,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         const uint32_t first = a.bin_base[tid] + excl;  // destination index of this tile's first key of bin tid
         if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[tid] = first + count;
         if (!DST) {
-            s_gbase[slot] = first - bin_start;  // mod 2^32; + tile position = destination index
+            s_gbase[tid] = first - bin_start;  // mod 2^32; + tile position = destination index
         } else {
             const uint64_t delta = 4ull * (uint64_t)first - 4ull * (uint64_t)bin_start;  // mod 2^64
-            reinterpret_cast<uint64_t *>(s_gbase)[slot] = a.bin_dst[tid] + delta;
-            if (PAIRS) reinterpret_cast<uint64_t *>(s_vbase)[slot] = a.bin_dst[B + tid] + delta;
+            reinterpret_cast<uint64_t *>(s_gbase)[tid] = a.bin_dst[tid] + delta;
+            if (PAIRS) reinterpret_cast<uint64_t *>(s_vbase)[tid] = a.bin_dst[B + tid] + delta;
         }
     }
     __syncthreads();
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             if (!DST) {
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
-                    if (k0 + g < ITEMS) gb[g] = sm_ld(sa_gbase | digit_slot(kk[g], rot, mask4));
+                    if (k0 + g < ITEMS) gb[g] = sm_ld(sa_gbase | (__funnelshift_r(kk[g], kk[g], rot) & mask4));
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g)
                     if (k0 + g < ITEMS) {
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                 for (int g = 0; g < kGroup; ++g)
                     if (k0 + g < ITEMS) {
                         const uint32_t j = tid + (k0 + g) * THREADS;
-                        const uint32_t d = digit_slot(kk[g], rot, mask4) >> 2;
+                        const uint32_t d = (__funnelshift_r(kk[g], kk[g], rot) & mask4) >> 2;
                         const uint64_t off = 4ull * j;
                         *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk[g];
                         if (PAIRS)
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
                 } else {
                     kk = sm_ld(sa_keys + 4u * j);
                 }
-                const uint32_t d4 = digit_slot(kk, rot, mask4);
+                const uint32_t d4 = __funnelshift_r(kk, kk, rot) & mask4;
                 if (!DST) {
                     const uint32_t g = sm_ld(sa_gbase | d4) + j;
                     kout[g] = kk;
