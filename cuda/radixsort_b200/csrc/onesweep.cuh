@@ -216,22 +216,39 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     }
 
     // ---- 2. count ---------------------------------------------------------------------------
+    // A warp is "clustered" when neighbouring lanes of its warp instructions mostly share digits
+    // (sorted or partially sorted input, few distinct keys, data grouped by earlier passes); four
+    // sample items decide.  Clustered warps rank runs of equal digits with one atomic (step 4) and
+    // use plain table slots -- they touch few distinct entries per instruction, so bank spreading
+    // (digit_slot) would only cost them instructions.
+    bool clustered = false;
+    if (MODE == RANK_ATOMIC) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) sm_inc(sa_wcnt | digit_slot(key[i], rot, mask4));
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t dq = __funnelshift_r(key[q * (ITEMS / 4)], key[q * (ITEMS / 4)], rot) & mask4;
+            const uint32_t heads = __ballot_sync(0xffffffffu, dq != __shfl_up_sync(0xffffffffu, dq, 1));
+            clustered = clustered || __popc(heads) <= 16;
+        }
+        if (lane == 0) s_hot[warp] = clustered ? 1u : 0u;
+    }
+    if (MODE == RANK_ATOMIC && clustered) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) sm_inc(sa_wcnt | (__funnelshift_r(key[i], key[i], rot) & mask4));
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) sm_inc(sa_wcnt | digit_slot(key[i], rot, mask4));
+    }
     __syncthreads();
 
     // ---- 3. offsets -------------------------------------------------------------------------
     uint32_t count = 0;
     uint32_t c[WARPS];
-    const uint32_t slot = fold_bin(tid);  // table entry of bin `tid` (see digit_slot)
+    const uint32_t folded = fold_bin(tid);  // table entry of bin `tid` in warps that use digit_slot
     if (tid < B) {
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
-            c[w] = s_cnt[w * B + slot];
+            c[w] = s_cnt[w * B + ((MODE == RANK_ATOMIC && s_hot[w]) ? tid : folded)];
             count += c[w];
-            // A digit holding >= 1/4 of a warp's keys marks that warp as clustered: its rank loop
-            // combines runs of equal digits before the atomic (see step 4).
-            if (MODE == RANK_ATOMIC && c[w] >= (uint32_t)(WARP_KEYS / 4)) s_hot[w] = (tid << 2) | 1u;
         }
     }
     const uint32_t st_not = ((2u * a.parity) & 3u) << 30;
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         uint32_t run = (MODE == RANK_ATOMIC) ? sa_keys + kSlot * bin_start : bin_start;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
-            s_cnt[w * B + slot] = run;
+            s_cnt[w * B + ((MODE == RANK_ATOMIC && s_hot[w]) ? tid : folded)] = run;
             run += (MODE == RANK_ATOMIC) ? kSlot * c[w] : c[w];
         }
     }
@@ -254,18 +271,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
     if (MODE == RANK_ATOMIC) {
-        // A warp is "clustered" when lanes of one warp instruction share digits: its hottest digit
-        // holds >= 1/4 of its keys (flag set in step 3), or neighbouring lanes of a sample item
-        // mostly agree (sorted / partially sorted input, data grouped by earlier passes).
         const uint32_t lt = lanemask_lt();
-        bool clustered = s_hot[warp] != 0u;
-        {
-            const uint32_t d0 = digit_slot(key[0], rot_fast, mask4);
-            const uint32_t d1 = digit_slot(key[ITEMS / 2], rot_fast, mask4);
-            const uint32_t h0 = __ballot_sync(0xffffffffu, d0 != __shfl_up_sync(0xffffffffu, d0, 1));
-            const uint32_t h1 = __ballot_sync(0xffffffffu, d1 != __shfl_up_sync(0xffffffffu, d1, 1));
-            clustered = clustered || __popc(h0) <= 16 || __popc(h1) <= 16;
-        }
         if (!clustered) {
             // Software-pipelined in groups: kGroup atomics in flight before their dependent stores,
             // so a warp pays one shared-memory round trip per group instead of one per key.
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t k = key[i];
-                const uint32_t d4 = digit_slot(k, rot_clustered, mask4);
+                const uint32_t d4 = __funnelshift_r(k, k, rot_clustered) & mask4;
                 const uint32_t prev = __shfl_up_sync(0xffffffffu, d4, 1);
                 const bool head = (lane == 0u) || (d4 != prev);
                 const uint32_t hm = __ballot_sync(0xffffffffu, head);        // bit 0 is always set
