@@ -217,15 +217,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 
     // ---- 2. count ---------------------------------------------------------------------------
     // A warp is "clustered" when neighbouring lanes of its warp instructions mostly share digits
-    // (sorted or partially sorted input, few distinct keys, data grouped by earlier passes); four
+    // (sorted or partially sorted input, few distinct keys, data grouped by earlier passes); two
     // sample items decide.  Clustered warps rank runs of equal digits with one atomic (step 4) and
     // use plain table slots -- they touch few distinct entries per instruction, so bank spreading
     // (digit_slot) would only cost them instructions.
     bool clustered = false;
     if (MODE == RANK_ATOMIC) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t dq = __funnelshift_r(key[q * (ITEMS / 4)], key[q * (ITEMS / 4)], rot) & mask4;
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t dq = __funnelshift_r(key[q * (ITEMS / 2)], key[q * (ITEMS / 2)], rot) & mask4;
             const uint32_t heads = __ballot_sync(0xffffffffu, dq != __shfl_up_sync(0xffffffffu, dq, 1));
             clustered = clustered || __popc(heads) <= 16;
         }
