@@ -129,7 +129,7 @@ struct PassTraits {
     static constexpr int OFF_GBASE = OFF_CNT + WARPS * B;                 // [B] or [B] x 64 bit
     static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);       // [B] x 64 bit (DST pairs)
     static constexpr int OFF_MASK = OFF_VBASE + ((DST && PAIRS) ? 2 * B : 0);  // [WARPS][2][TABLE]
-    static constexpr int OFF_HOT = OFF_MASK + WARPS * 2 * TABLE;          // [WARPS] hot digit of each warp (0 = none)
+    static constexpr int OFF_HOT = (OFF_MASK + WARPS * 2 * TABLE + 3) / 4 * 4;  // [WARPS] 1 = clustered warp (16-byte aligned)
     static constexpr int OFF_MISC = OFF_HOT + ((WARPS + 3) / 4) * 4;      // warp totals[32]
     static constexpr int SMEM_WORDS = OFF_MISC + 36;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
@@ -244,10 +244,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t count = 0;
     uint32_t c[WARPS];
     const uint32_t folded = fold_bin(tid);  // table entry of bin `tid` in warps that use digit_slot
+    uint32_t plain_mask = 0;                // bit w: warp w is clustered and uses plain slots
+    if (MODE == RANK_ATOMIC && tid < B) {
+#pragma unroll
+        for (int w4 = 0; w4 < (WARPS + 3) / 4; ++w4) {
+            const uint4 f = reinterpret_cast<const uint4 *>(s_hot)[w4];  // broadcast loads
+            plain_mask |= (f.x | (f.y << 1) | (f.z << 2) | (f.w << 3)) << (4 * w4);
+        }
+    }
     if (tid < B) {
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
-            c[w] = s_cnt[w * B + ((MODE == RANK_ATOMIC && s_hot[w]) ? tid : folded)];
+            c[w] = s_cnt[w * B + ((plain_mask >> w & 1u) ? tid : folded)];
             count += c[w];
         }
     }
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         uint32_t run = (MODE == RANK_ATOMIC) ? sa_keys + kSlot * bin_start : bin_start;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) {
-            s_cnt[w * B + ((MODE == RANK_ATOMIC && s_hot[w]) ? tid : folded)] = run;
+            s_cnt[w * B + ((plain_mask >> w & 1u) ? tid : folded)] = run;
             run += (MODE == RANK_ATOMIC) ? kSlot * c[w] : c[w];
         }
     }
