@@ -49,16 +49,16 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a)
 
     uint32_t *col = s_hist + lane;  // this lane's column
     auto tally = [&](uint32_t key) {
-        if (P_CT < 0) {
+        if constexpr (P_CT < 0) {
             atomicAdd(col + (((key >> shift0) & mask0) << 5), 1u);
-            return;
-        }
+        } else {
 #pragma unroll
-        for (int p = 0; p < (P_CT > 0 ? P_CT : kMaxPasses); ++p) {
-            if (P_CT == 0 && p >= P) break;
-            const uint32_t d = P_CT > 0 ? ((key >> (p * W)) & (B - 1))
-                                        : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
-            atomicAdd(col + ((p * B + d) << 5), 1u);
+            for (int p = 0; p < (P_CT > 0 ? P_CT : kMaxPasses); ++p) {
+                if (P_CT == 0 && p >= P) break;
+                const uint32_t d = P_CT > 0 ? ((key >> (p * W)) & (B - 1))
+                                            : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
+                atomicAdd(col + ((p * B + d) << 5), 1u);
+            }
         }
     };
 

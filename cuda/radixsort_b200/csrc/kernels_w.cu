@@ -1,5 +1,7 @@
 // kernels_w.cu -- instantiates the histogram and digit-pass kernels for ONE digit width.
 // Compiled eight times (-DB200_W=1 .. 8) so the widths build in parallel.
+#include <algorithm>
+
 #include "hist.cuh"
 #include "launch.h"
 #include "onesweep.cuh"
@@ -20,7 +22,7 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
     constexpr int TB = g.table_bits;
     using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
-    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, PAIRS, DST>;
+    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, (g.persist != 0), PAIRS, DST>;
     static uint64_t configured = 0;  // one bit per device: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -30,7 +32,21 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured |= 1ull << (dev & 63);
     }
-    kernel<<<a.num_tiles, g.threads, TR::SMEM_BYTES, s>>>(a);
+    unsigned grid = a.num_tiles;
+    if (g.persist) {
+        // every CTA of a persistent launch must be resident: the look-back spins on tiles that
+        // belong to other CTAs of the same launch
+        static int resident[64] = {};
+        if (resident[dev & 63] == 0) {
+            int per_sm = 0, sms = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, TR::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            resident[dev & 63] = std::max(1, std::min(per_sm, g.min_ctas) * sms);
+        }
+        grid = std::min<unsigned>(grid, (unsigned)resident[dev & 63]);
+    }
+    kernel<<<grid, g.threads, TR::SMEM_BYTES, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -105,6 +121,9 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 25: return launch_modes<25>(pairs, dst, a, s);
     case 26: return launch_modes<26>(pairs, dst, a, s);
     case 27: return launch_modes<27>(pairs, dst, a, s);
+    case 29: return launch_modes<29>(pairs, dst, a, s);
+    case 30: return launch_modes<30>(pairs, dst, a, s);
+    case 31: return launch_modes<31>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

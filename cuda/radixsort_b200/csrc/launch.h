@@ -16,38 +16,42 @@ struct PassVariant {
     int mode;
     int table_bits;
     int lb_batch;  // look-back descriptors in flight per bin thread
+    int persist;   // 1: persistent CTAs that prefetch their next tile
 };
-constexpr int kNumVariants = 29;
+constexpr int kNumVariants = 32;
 constexpr PassVariant kVariants[kNumVariants] = {
-    {256, 30, 20, 4, 0, 5, 8},   //  0 default: table(5 bits) + 3 ballots
-    {256, 30, 20, 4, 1, 0, 8},   //  1 atomic rank (selected only after the self test passes)
-    {256, 36, 24, 4, 0, 5, 8},   //  2
-    {256, 36, 20, 4, 1, 0, 8},   //  3
-    {384, 20, 14, 3, 0, 5, 8},   //  4
-    {384, 20, 14, 3, 1, 0, 8},   //  5
-    {256, 30, 20, 4, 0, 8, 8},   //  6 full-digit atomicOr table, no ballots
-    {256, 30, 20, 4, 0, 6, 8},   //  7 table(6 bits) + 2 ballots
-    {384, 20, 14, 2, 2, 0, 8},   //  8 match.any (for the record)
-    {256, 40, 24, 3, 1, 0, 8},   //  9
-    {256, 44, 22, 3, 1, 0, 8},   // 10
-    {512, 36, 24, 2, 1, 0, 8},   // 11
-    {512, 24, 16, 3, 1, 0, 8},   // 12
-    {384, 32, 20, 3, 1, 0, 8},   // 13
-    {384, 24, 16, 3, 1, 0, 8},   // 14
-    {512, 30, 20, 2, 1, 0, 8},   // 15
-    {256, 30, 20, 4, 0, 0, 8},   // 16 ballots only (narrow digits); instantiated for every width
-    {256, 44, 22, 3, 1, 0, 4},   // 17 = 10 with a 4-deep look-back
-    {256, 44, 22, 3, 1, 0, 16},  // 18 = 10 with a 16-deep look-back
-    {384, 44, 22, 2, 1, 0, 8},   // 19
-    {512, 22, 12, 3, 1, 0, 8},   // 20
-    {384, 30, 16, 3, 1, 0, 8},   // 21
-    {256, 44, 22, 4, 1, 0, 8},   // 22 = 10 at four CTAs per SM
-    {256, 40, 20, 4, 1, 0, 8},   // 23
-    {256, 52, 26, 3, 1, 0, 8},   // 24
-    {256, 60, 30, 3, 1, 0, 8},   // 25
-    {256, 64, 32, 2, 1, 0, 8},   // 26
-    {256, 48, 24, 3, 1, 0, 8},   // 27
-    {256, 16, 12, 6, 0, 0, 8},   // 28 ballots only, small tile / high occupancy (fused exchange experiments)
+    {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
+    {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
+    {256, 36, 24, 4, 0, 5, 8, 0},   //  2
+    {256, 36, 20, 4, 1, 0, 8, 0},   //  3
+    {384, 20, 14, 3, 0, 5, 8, 0},   //  4
+    {384, 20, 14, 3, 1, 0, 8, 0},   //  5
+    {256, 30, 20, 4, 0, 8, 8, 0},   //  6 full-digit atomicOr table, no ballots
+    {256, 30, 20, 4, 0, 6, 8, 0},   //  7 table(6 bits) + 2 ballots
+    {384, 20, 14, 2, 2, 0, 8, 0},   //  8 match.any (for the record)
+    {256, 40, 24, 3, 1, 0, 8, 0},   //  9
+    {256, 44, 22, 3, 1, 0, 8, 0},   // 10
+    {512, 36, 24, 2, 1, 0, 8, 0},   // 11
+    {512, 24, 16, 3, 1, 0, 8, 0},   // 12
+    {384, 32, 20, 3, 1, 0, 8, 0},   // 13
+    {384, 24, 16, 3, 1, 0, 8, 0},   // 14
+    {512, 30, 20, 2, 1, 0, 8, 0},   // 15
+    {256, 30, 20, 4, 0, 0, 8, 0},   // 16 ballots only (narrow digits); instantiated for every width
+    {256, 44, 22, 3, 1, 0, 4, 0},   // 17 = 10 with a 4-deep look-back
+    {256, 44, 22, 3, 1, 0, 16, 0},  // 18 = 10 with a 16-deep look-back
+    {384, 44, 22, 2, 1, 0, 8, 0},   // 19
+    {512, 22, 12, 3, 1, 0, 8, 0},   // 20
+    {384, 30, 16, 3, 1, 0, 8, 0},   // 21
+    {256, 44, 22, 4, 1, 0, 8, 0},   // 22 = 10 at four CTAs per SM
+    {256, 40, 20, 4, 1, 0, 8, 0},   // 23
+    {256, 52, 26, 3, 1, 0, 8, 0},   // 24
+    {256, 60, 30, 3, 1, 0, 8, 0},   // 25
+    {256, 64, 32, 2, 1, 0, 8, 0},   // 26
+    {256, 48, 24, 3, 1, 0, 8, 0},   // 27
+    {256, 16, 12, 6, 0, 0, 8, 0},   // 28 ballots only, small tile / high occupancy (fused exchange experiments)
+    {256, 44, 22, 3, 1, 0, 8, 1},   // 29 = 10, persistent
+    {256, 44, 22, 2, 1, 0, 8, 1},   // 30 persistent, two CTAs per SM
+    {256, 36, 20, 4, 1, 0, 8, 1},   // 31 persistent, four CTAs per SM
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

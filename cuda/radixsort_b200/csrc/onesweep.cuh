@@ -138,7 +138,7 @@ struct PassTraits {
 
 constexpr int kGroup = 6;  // shared-memory operations in flight per thread in the rank / write-out loops
 
-template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, int LB, bool PAIRS, bool DST>
+template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, int LB, bool PERSIST, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
     constexpr int kLookbackBatch = LB;  // descriptors in flight per bin thread during the look-back
     using TR = PassTraits<W, THREADS, ITEMS, MODE, TB, PAIRS, DST>;
@@ -165,18 +165,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     const uint32_t sa_keys = smem_u32(s_keys);
     const uint32_t sa_wcnt = smem_u32(s_cnt + warp * B);  // multiple of 4*B bytes
 
-    {
-        // s_cnt .. s_mask are contiguous and 16-byte aligned; rounding the vector count up spills
-        // at most 3 words into s_warp_tot, which is written before it is read.
-        uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
-        constexpr int ZV = (TR::OFF_MISC - TR::OFF_CNT + 3) / 4;
-        for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    const uint32_t tile = blockIdx.x;
-    const uint32_t tile_base = tile * (uint32_t)TILE;
-    const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
-    const bool full = (n_valid == (uint32_t)TILE);
     // byte offset of a key's digit inside a 4-byte-entry table: (rotr(key, shift-2) & mask4).
     // Every phase uses its own laundered copy of the rotate amount (see launder()).
     const uint32_t rot = (a.shift + 30u) & 31u;
@@ -188,24 +176,26 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t key[ITEMS];
     uint32_t val[PAIRS ? ITEMS : 1];
     const uint32_t woff = warp * WARP_KEYS + lane;
-    if (full) {
-        const uint32_t *src = a.keys_in + tile_base + woff;
+    auto load_full = [&](uint32_t t) {
+        const uint32_t *src = a.keys_in + t * (uint32_t)TILE + woff;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) key[i] = ld_stream(src + i * 32);
         if (PAIRS) {
-            const uint32_t *vsrc = a.vals_in + tile_base + woff;
+            const uint32_t *vsrc = a.vals_in + t * (uint32_t)TILE + woff;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) val[i] = ld_stream(vsrc + i * 32);
         }
-    } else {
-        // Ragged last tile (once per launch): staged through shared memory so that the path above
-        // stays free of per-item predicates.  Out-of-range items become all-ones keys: they fall
-        // in the highest occupied bin, after every real key of the tile, i.e. at tile positions
-        // >= n_valid, and are never written out.
+    };
+    // Ragged last tile (once per launch): staged through shared memory so that the path above
+    // stays free of per-item predicates.  Out-of-range items become all-ones keys: they fall in
+    // the highest occupied bin, after every real key of the tile, i.e. at tile positions
+    // >= n_valid, and are never written out.  Must be called by the whole CTA.
+    auto load_staged = [&](uint32_t t, uint32_t nv) {
+        const uint32_t tb = t * (uint32_t)TILE;
 #pragma unroll 1
         for (uint32_t j = tid; j < (uint32_t)TILE; j += THREADS) {
-            s_keys[j] = (j < n_valid) ? a.keys_in[tile_base + j] : 0xFFFFFFFFu;
-            if (PAIRS) s_vals[j] = (j < n_valid) ? a.vals_in[tile_base + j] : 0u;
+            s_keys[j] = (j < nv) ? a.keys_in[tb + j] : 0xFFFFFFFFu;
+            if (PAIRS) s_vals[j] = (j < nv) ? a.vals_in[tb + j] : 0u;
         }
         __syncthreads();
 #pragma unroll
@@ -213,7 +203,29 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             key[i] = s_keys[woff + i * 32];
             if (PAIRS) val[i] = s_vals[woff + i * 32];
         }
+        __syncthreads();
+    };
+
+    // PERSIST: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and issues the loads of
+    // its next tile as soon as the rank phase has emptied the key registers, so they are in flight
+    // during the look-back and the write-out of the current tile.
+    uint32_t tile = blockIdx.x;
+    {
+        const uint32_t nv = min((uint32_t)TILE, a.n - tile * (uint32_t)TILE);
+        if (nv == (uint32_t)TILE) load_full(tile); else load_staged(tile, nv);
     }
+    for (;;) {
+    const uint32_t tile_base = tile * (uint32_t)TILE;
+    const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
+    const bool full = (n_valid == (uint32_t)TILE);
+    {
+        // s_cnt .. s_mask are contiguous and 16-byte aligned; rounding the vector count up spills
+        // at most 3 words into s_warp_tot, which is written before it is read.
+        uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
+        constexpr int ZV = (TR::OFF_MISC - TR::OFF_CNT + 3) / 4;
+        for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
 
     // ---- 2. count ---------------------------------------------------------------------------
     // A warp is "clustered" when neighbouring lanes of its warp instructions mostly share digits
@@ -361,6 +373,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         }
     }
 
+    // ---- next tile's loads (PERSIST): the key registers are free from here on ----------------------
+    uint32_t next_tile = tile;
+    bool has_next = false, next_full = false;
+    if (PERSIST) {
+        next_tile = tile + gridDim.x;
+        has_next = next_tile < a.num_tiles;
+        next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
+        if (next_full) load_full(next_tile);
+    }
+
     // ---- 5. decoupled look-back: one thread per bin, kLookbackBatch descriptors in flight ------
     if (tid < B) {
         uint32_t excl = 0;
@@ -470,6 +492,12 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             }
         }
     }
+
+    if (!PERSIST || !has_next) break;
+    __syncthreads();  // the write-out has finished reading s_keys / s_gbase before they are reused
+    if (!next_full) load_staged(next_tile, a.n - next_tile * (uint32_t)TILE);
+    tile = next_tile;
+    }  // tile loop
 }
 
 // ---- self test for RANK_ATOMIC ------------------------------------------------------------------
