@@ -110,8 +110,8 @@ struct Layout {
     uint64_t total_tiles;
     uint64_t portion_tiles;  // tiles per launch
     uint64_t portions;
-    // zeroed header: done | zeros[bins] | ghist[passes * bins]
-    size_t off_done, off_zeros, off_ghist, header_bytes;
+    // zeroed header: tickets[passes * portions] | done | zeros[bins] | ghist[passes * bins]
+    size_t off_tickets, off_done, off_zeros, off_ghist, header_bytes;
     size_t off_bin_base;  // [passes][2][bins]
     size_t off_desc;      // [total_tiles][bins]
     size_t desc_bytes;
@@ -132,6 +132,7 @@ Layout make_layout(uint64_t n, int passes, int width, bool pairs, bool need_alt,
     L.portion_tiles = std::max<uint64_t>(1, std::min<uint64_t>(cap, std::max<uint64_t>(L.total_tiles, 1)));
     L.portions = std::max<uint64_t>(1, (L.total_tiles + L.portion_tiles - 1) / L.portion_tiles);
     size_t off = 0;
+    L.off_tickets = off;  off += align_up((size_t)passes * L.portions * 4, 16);
     L.off_done = off;     off += 16;
     L.off_zeros = off;    off += (size_t)L.bins * 4;
     L.off_ghist = off;    off += (size_t)passes * L.bins * 4;
@@ -191,7 +192,10 @@ size_t temp_upper_bound(uint64_t n, int nbits, bool pairs) {
     PassList pl;
     if (!build_pass_list(nbits, pl)) return 0;
     Layout L = make_layout(n, pl.count, pl.width, pairs, true, kMinTileKeys, 0);
-    return L.total + 4096;
+    size_t tickets = 0;  // a forced small portion size (tests) multiplies the launches per pass
+    if (g_params.portion_tiles > 0)
+        tickets = (size_t)pl.count * (((n + kMinTileKeys - 1) / kMinTileKeys) / g_params.portion_tiles + 2) * 4;
+    return L.total + align_up(tickets, 256) + 4096;
 }
 
 // ---- profiling events --------------------------------------------------------------------------
@@ -321,6 +325,7 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
             a.bin_base = bin_base + ((size_t)(2 * p) + (q & 1)) * L.bins;
             a.carry_out = (q + 1 < L.portions) ? bin_base + ((size_t)(2 * p) + ((q + 1) & 1)) * L.bins : nullptr;
             a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
+            a.ticket = reinterpret_cast<uint32_t *>(base + L.off_tickets) + (size_t)p * L.portions + q;
             a.bin_dst = nullptr;
             a.n = (uint32_t)count;
             a.num_tiles = (uint32_t)((count + tile - 1) / tile);
@@ -759,6 +764,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
         a.bin_base = bin_base + (q & 1) * L.bins;
         a.carry_out = (q + 1 < L.portions) ? bin_base + ((q + 1) & 1) * L.bins : nullptr;
         a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
+        a.ticket = reinterpret_cast<uint32_t *>(base + L.off_tickets) + q;
         a.bin_dst = d_bin_dst;
         a.n = (uint32_t)count;
         a.num_tiles = (uint32_t)((count + tile - 1) / tile);

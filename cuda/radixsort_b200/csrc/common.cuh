@@ -44,6 +44,7 @@ struct PassArgs {
     const uint32_t *bin_base;  // [2^width] destination index of the first key of each bin
     uint32_t *carry_out;       // [2^width] bin_base of the next launch of this pass, or null
     uint32_t *desc;            // [num_tiles][2^width] look-back descriptors
+    uint32_t *ticket;          // zeroed tile counter of this launch (persistent variants only)
     const uint64_t *bin_dst;   // optional [2 * 2^width] per-bin destination addresses
     uint32_t n;                // keys in this launch (< 2^30)
     uint32_t num_tiles;

@@ -206,15 +206,28 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         __syncthreads();
     };
 
-    // PERSIST: the CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and issues the loads of
-    // its next tile as soon as the rank phase has emptied the key registers, so they are in flight
-    // during the look-back and the write-out of the current tile.
+    // PERSIST: the CTA takes tiles from an atomic ticket (dynamic order keeps the tiles in flight
+    // staggered, which the look-back needs; a static stride would start a whole round of tiles in
+    // lockstep) and issues the loads of its next tile as soon as the rank phase has emptied the key
+    // registers, so they are in flight during the look-back and the write-out of the current tile.
+    // The ticket for the next tile is requested at the top of an iteration and published to the CTA
+    // just before the barrier that ends the offsets phase.
+    uint32_t *s_next = smem + TR::OFF_MISC + 32;
     uint32_t tile = blockIdx.x;
+    if (PERSIST) {
+        if (tid == 0) *s_next = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        tile = *s_next;
+        if (tile >= a.num_tiles) return;  // more CTAs than tiles
+        __syncthreads();
+    }
     {
         const uint32_t nv = min((uint32_t)TILE, a.n - tile * (uint32_t)TILE);
         if (nv == (uint32_t)TILE) load_full(tile); else load_staged(tile, nv);
     }
     for (;;) {
+    uint32_t ticket = 0;
+    if (PERSIST && tid == 0) ticket = atomicAdd(a.ticket, 1u);  // consumed in step 3
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
@@ -287,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
             run += (MODE == RANK_ATOMIC) ? kSlot * c[w] : c[w];
         }
     }
+    if (PERSIST && tid == 0) *s_next = ticket;
     __syncthreads();
 
     // ---- 4. rank + reorder through shared memory ----------------------------------------------
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t next_tile = tile;
     bool has_next = false, next_full = false;
     if (PERSIST) {
-        next_tile = tile + gridDim.x;
+        next_tile = *s_next;
         has_next = next_tile < a.num_tiles;
         next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
         if (next_full) load_full(next_tile);
