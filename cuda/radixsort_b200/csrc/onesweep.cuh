@@ -387,16 +387,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         }
     }
 
-    // ---- next tile's loads (PERSIST): the key registers are free from here on ----------------------
-    uint32_t next_tile = tile;
-    bool has_next = false, next_full = false;
-    if (PERSIST) {
-        next_tile = *s_next;
-        has_next = next_tile < a.num_tiles;
-        next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
-        if (next_full) load_full(next_tile);
-    }
-
     // ---- 5. decoupled look-back: one thread per bin, kLookbackBatch descriptors in flight ------
     if (tid < B) {
         uint32_t excl = 0;
@@ -434,6 +424,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         }
     }
     __syncthreads();
+
+    // ---- next tile's loads (PERSIST).  The key registers have been free since the rank phase, but
+    // issuing the loads before the look-back queues 350 requests in front of its descriptor reads
+    // (measured: 0.69 vs 0.64 ms per pass); here they overlap the write-out only.
+    uint32_t next_tile = tile;
+    bool has_next = false, next_full = false;
+    if (PERSIST) {
+        next_tile = *s_next;
+        has_next = next_tile < a.num_tiles;
+        next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
+        if (next_full) load_full(next_tile);
+    }
 
     // ---- 6. write out -------------------------------------------------------------------------
     const uint32_t sa_gbase = smem_u32(s_gbase);
