@@ -387,6 +387,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         }
     }
 
+    // ---- next tile's loads (PERSIST): the key registers are free from here on.  Measured on B200
+    // (profiles/r01_sweep_v8_persistent.jsonl): 0.69 ms per pass against 0.64 for one tile per CTA --
+    // the 350 load requests queue in front of the look-back's descriptor reads; issuing them after
+    // the look-back instead (overlapping only the write-out) is worse still (1.03 ms).  The
+    // persistent variants are kept as measured experiments, not as the default.
+    uint32_t next_tile = tile;
+    bool has_next = false, next_full = false;
+    if (PERSIST) {
+        next_tile = *s_next;
+        has_next = next_tile < a.num_tiles;
+        next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
+        if (next_full) load_full(next_tile);
+    }
+
     // ---- 5. decoupled look-back: one thread per bin, kLookbackBatch descriptors in flight ------
     if (tid < B) {
         uint32_t excl = 0;
@@ -424,18 +438,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         }
     }
     __syncthreads();
-
-    // ---- next tile's loads (PERSIST).  The key registers have been free since the rank phase, but
-    // issuing the loads before the look-back queues 350 requests in front of its descriptor reads
-    // (measured: 0.69 vs 0.64 ms per pass); here they overlap the write-out only.
-    uint32_t next_tile = tile;
-    bool has_next = false, next_full = false;
-    if (PERSIST) {
-        next_tile = *s_next;
-        has_next = next_tile < a.num_tiles;
-        next_full = has_next && (a.n - next_tile * (uint32_t)TILE >= (uint32_t)TILE);
-        if (next_full) load_full(next_tile);
-    }
 
     // ---- 6. write out -------------------------------------------------------------------------
     const uint32_t sa_gbase = smem_u32(s_gbase);
