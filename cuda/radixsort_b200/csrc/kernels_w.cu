@@ -22,7 +22,7 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
     constexpr int TB = g.table_bits;
     using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
-    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, (g.persist != 0), PAIRS, DST>;
+    auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, (g.persist == 1), (g.persist == 2), PAIRS, DST>;
     static uint64_t configured = 0;  // one bit per device: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -33,7 +33,7 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
         configured |= 1ull << (dev & 63);
     }
     unsigned grid = a.num_tiles;
-    if (g.persist) {
+    if (g.persist == 1) {
         // every CTA of a persistent launch must be resident: the look-back spins on tiles that
         // belong to other CTAs of the same launch
         static int resident[64] = {};
@@ -124,6 +124,8 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 29: return launch_modes<29>(pairs, dst, a, s);
     case 30: return launch_modes<30>(pairs, dst, a, s);
     case 31: return launch_modes<31>(pairs, dst, a, s);
+    case 32: return launch_modes<32>(pairs, dst, a, s);
+    case 33: return launch_modes<33>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -16,9 +16,9 @@ struct PassVariant {
     int mode;
     int table_bits;
     int lb_batch;  // look-back descriptors in flight per bin thread
-    int persist;   // 1: persistent CTAs that prefetch their next tile
+    int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA
 };
-constexpr int kNumVariants = 32;
+constexpr int kNumVariants = 34;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -52,6 +52,8 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 44, 22, 3, 1, 0, 8, 1},   // 29 = 10, persistent
     {256, 44, 22, 2, 1, 0, 8, 1},   // 30 persistent, two CTAs per SM
     {256, 36, 20, 4, 1, 0, 8, 1},   // 31 persistent, four CTAs per SM
+    {256, 44, 22, 3, 1, 0, 8, 2},   // 32 = 10 with TMA bulk loads of the tile
+    {256, 36, 20, 4, 1, 0, 8, 2},   // 33 TMA, four CTAs per SM
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

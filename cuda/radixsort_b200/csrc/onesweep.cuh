@@ -138,7 +138,7 @@ struct PassTraits {
 
 constexpr int kGroup = 6;  // shared-memory operations in flight per thread in the rank / write-out loops
 
-template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, int LB, bool PERSIST, bool PAIRS, bool DST>
+template <int W, int THREADS, int ITEMS, int MIN_CTAS, int MODE, int TB, int LB, bool PERSIST, bool TMA, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const PassArgs a) {
     constexpr int kLookbackBatch = LB;  // descriptors in flight per bin thread during the look-back
     using TR = PassTraits<W, THREADS, ITEMS, MODE, TB, PAIRS, DST>;
@@ -176,6 +176,28 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
     uint32_t key[ITEMS];
     uint32_t val[PAIRS ? ITEMS : 1];
     const uint32_t woff = warp * WARP_KEYS + lane;
+    // TMA: the tile is fetched by the bulk-copy engine (cp.async.bulk -> SASS UBLKCP) into the
+    // reorder buffer and read from there, so the 350 key-load requests of a tile do not sit in the
+    // SM's load/store queue in front of other CTAs' look-back reads and stores.  Needs 16-byte
+    // aligned inputs; otherwise (and for a ragged tile) the LDG paths are used.
+    __shared__ __align__(8) uint64_t s_bar;
+    const bool use_tma = TMA && !PERSIST && ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0) &&
+                         (!PAIRS || (reinterpret_cast<uintptr_t>(a.vals_in) & 15u) == 0);
+    auto load_tma_issue = [&](uint32_t t) {  // thread 0 only
+        constexpr uint32_t kParts = 8, kPartBytes = TILE * 4 / kParts;
+        static_assert((TILE * 4) % (kParts * 16) == 0, "bulk copies move multiples of 16 bytes");
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&s_bar, (PAIRS ? 2u : 1u) * TILE * 4u);
+#pragma unroll
+        for (uint32_t q = 0; q < kParts; ++q) {
+            bulk_g2s(reinterpret_cast<char *>(s_keys) + q * kPartBytes,
+                     reinterpret_cast<const char *>(a.keys_in + t * (uint32_t)TILE) + q * kPartBytes, kPartBytes, &s_bar);
+            if (PAIRS)
+                bulk_g2s(reinterpret_cast<char *>(s_vals) + q * kPartBytes,
+                         reinterpret_cast<const char *>(a.vals_in + t * (uint32_t)TILE) + q * kPartBytes, kPartBytes, &s_bar);
+        }
+    };
     auto load_full = [&](uint32_t t) {
         const uint32_t *src = a.keys_in + t * (uint32_t)TILE + woff;
 #pragma unroll
@@ -221,9 +243,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         if (tile >= a.num_tiles) return;  // more CTAs than tiles
         __syncthreads();
     }
+    bool tma_pending = false;
     {
         const uint32_t nv = min((uint32_t)TILE, a.n - tile * (uint32_t)TILE);
-        if (nv == (uint32_t)TILE) load_full(tile); else load_staged(tile, nv);
+        if (nv != (uint32_t)TILE) {
+            load_staged(tile, nv);
+        } else if (use_tma) {
+            if (tid == 0) load_tma_issue(tile);
+            tma_pending = true;
+        } else {
+            load_full(tile);
+        }
     }
     for (;;) {
     uint32_t ticket = 0;
@@ -239,6 +269,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
         for (int i = tid; i < ZV; i += THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
+    if (TMA && tma_pending) {  // block-uniform
+        mbar_wait(&s_bar, 0);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            key[i] = s_keys[woff + i * 32];
+            if (PAIRS) val[i] = s_vals[woff + i * 32];
+        }
+        tma_pending = false;  // s_keys is rewritten two barriers later (rank phase)
+    }
 
     // ---- 2. count ---------------------------------------------------------------------------
     // A warp is "clustered" when neighbouring lanes of its warp instructions mostly share digits
