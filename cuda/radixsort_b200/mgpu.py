@@ -218,12 +218,37 @@ class ShardedSorter:
         t.marks = []
         t.mark("start")
 
-        hist = ops.histogram(keys, shift, TOP_BITS)                     # device, uint32 counts as int32
+        # Partition digit = the highest 8-bit window in which the keys differ: when every key of every
+        # rank shares the window's value (small-range keys: constant high bytes) the window moves down
+        # one byte and the histogram is taken again -- the higher bytes are then equal for all keys, so
+        # the lower window still defines a range partition.  Uniform keys never take a second round.
+        while True:
+            hist = ops.histogram(keys, shift, TOP_BITS)                 # device, uint32 counts as int32
+            counts = hist.to(torch.int64) & 0xFFFFFFFF
+            gathered = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
+            dist.all_gather_into_tensor(gathered, counts, group=self.group)
+            counts_all = gathered.cpu().numpy().reshape(world, -1)      # sync point: split sizes live on the host
+            if shift == 0 or np.count_nonzero(counts_all.sum(axis=0)) > 1:
+                break
+            shift -= TOP_BITS
         t.mark("histogram")
-        counts = hist.to(torch.int64) & 0xFFFFFFFF
-        gathered = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
-        dist.all_gather_into_tensor(gathered, counts, group=self.group)
-        counts_all = gathered.cpu().numpy().reshape(world, -1)          # sync point: split sizes live on the host
+        self.partition_shift = shift
+        if np.count_nonzero(counts_all.sum(axis=0)) <= 1:
+            # all keys are equal: every shard already is a slice of the sorted array, in global input
+            # order (which is what stability asks of equal keys) -- nothing to exchange
+            plan = plan_exchange(counts_all, rank)
+            plan["identity"] = True
+            self.last_plan = plan
+            if self.out is None or self.out.numel() < n_local:
+                self.out = ops.empty(max(n_local, 1))
+            self.out[:n_local].copy_(keys)
+            t.mark("local_sort")
+            if vals is None:
+                return self.out[:n_local]
+            if self.out_v is None or self.out_v.numel() < n_local:
+                self.out_v = ops.empty(max(n_local, 1))
+            self.out_v[:n_local].copy_(vals)
+            return self.out[:n_local], self.out_v[:n_local]
         plan = plan_exchange(counts_all, rank)
         self.last_plan = plan
         need = int(plan["totals"].max())
@@ -237,7 +262,7 @@ class ShardedSorter:
 
         my_total = plan["my_total"]
         pbits = plan["narrow_bits"] if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
-        pshift = 32 - pbits
+        pshift = shift + TOP_BITS - pbits
         if self.fused:
             # partition + exchange in one kernel: every bin is stored straight into its owner's buffer
             if pbits == TOP_BITS:
@@ -327,6 +352,7 @@ class ShardedSorter:
             rep["exchange"] = "fused peer stores" if self.fused else "nccl all_to_all_single"
             rep["partition_bits"] = int(plan["narrow_bits"]) if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
             rep["shard_sizes"] = [int(x) for x in plan["totals"]]
+            rep["partition_shift"] = int(getattr(self, "partition_shift", 32 - TOP_BITS))
         return rep
 
 

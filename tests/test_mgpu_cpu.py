@@ -110,6 +110,15 @@ def _np_verify(t):
     return int(np.count_nonzero(k[:-1] > k[1:])), s, h, x
 
 
+def _make(O, kind, count, first, total):
+    """small16 / small8: uniform keys with constant (zero) high bytes -- the partition digit must move down."""
+    if kind == "small16":
+        return O.generate("uniform", count, first=first, total=total) & np.uint32(0xFFFF)
+    if kind == "small8":
+        return O.generate("uniform", count, first=first, total=total) & np.uint32(0xFF)
+    return O.generate(kind, count, first=first, total=total)
+
+
 def _worker(rank, world, port, kind, n_total, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -118,14 +127,18 @@ def _worker(rank, world, port, kind, n_total, out_dir):
     per = n_total // world
     first = rank * per
     count = per if rank < world - 1 else n_total - first
-    keys = torch.from_numpy(O.generate(kind, count, first=first, total=n_total).view(np.int32))
+    keys = torch.from_numpy(_make(O, kind, count, first, n_total).view(np.int32))
     sorter = mgpu.ShardedSorter(dist.group.WORLD, nbits=8, ops=NumpyOps(), time_phases=False)
     res = sorter.sort(keys)
+    key_shift = sorter.partition_shift
     ok = mgpu.verify_sharded(res, keys, verify_fn=_np_verify)
     # a corrupted shard must be caught
     if res.numel() > 2:
         broken = res.clone()
-        broken[0], broken[-1] = res[-1], res[0]
+        if int(res[0]) != int(res[-1]):
+            broken[0], broken[-1] = res[-1], res[0]        # order violation
+        else:
+            broken[0] = int(res[0]) ^ 1                     # constant shard: change the multiset instead
         caught = not mgpu.verify_sharded(broken, keys, verify_fn=_np_verify)
     else:
         caught = not mgpu.verify_sharded(torch.cat([res, res.new_zeros(1)]), keys, verify_fn=_np_verify)
@@ -136,7 +149,7 @@ def _worker(rank, world, port, kind, n_total, out_dir):
     pk, pv = sorter.sort_pairs(kk, vv)
     np.save(os.path.join(out_dir, f"pairs_k{rank}.npy"), pk.numpy().view(np.uint32).copy())
     np.save(os.path.join(out_dir, f"pairs_v{rank}.npy"), pv.numpy().view(np.uint32).copy())
-    np.save(os.path.join(out_dir, f"flags{rank}.npy"), np.array([ok, caught]))
+    np.save(os.path.join(out_dir, f"flags{rank}.npy"), np.array([ok, caught, key_shift]))
     dist.destroy_process_group()
 
 
@@ -147,19 +160,21 @@ def _free_port():
 
 
 @pytest.mark.parametrize("kind,n_total", [("uniform", 200003), ("zipf", 120001), ("all_equal", 5000),
-                                          ("sorted", 70000)])
+                                          ("sorted", 70000), ("small16", 90001), ("small8", 30000)])
 def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     import oracle as O
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), kind, n_total, str(tmp_path)), nprocs=world, join=True)
     shards = [np.load(tmp_path / f"shard{r}.npy") for r in range(world)]
     flags = [np.load(tmp_path / f"flags{r}.npy") for r in range(world)]
-    whole = O.generate(kind, n_total, total=n_total)
+    whole = _make(O, kind, n_total, 0, n_total)
     assert np.array_equal(np.concatenate(shards), O.sort_keys(whole, 8))       # concatenation in rank order
     assert all(f[0] for f in flags), "verify_sharded rejected a correct result"
     assert all(f[1] for f in flags), "verify_sharded accepted a corrupted result"
-    if kind == "uniform":
-        assert abs(len(shards[0]) - len(shards[1])) < 0.02 * n_total              # balanced split
+    if kind in ("uniform", "small16", "small8", "all_equal"):
+        assert abs(len(shards[0]) - len(shards[1])) < 0.02 * n_total + 2          # balanced split
+    expected_shift = {"small16": 8, "small8": 0, "all_equal": 0}.get(kind, 24)
+    assert all(int(f[2]) == expected_shift for f in flags)                        # partition digit moved down
     # pairs: concatenation == stable sort of (masked key, global index)
     pk = np.concatenate([np.load(tmp_path / f"pairs_k{r}.npy") for r in range(world)])
     pv = np.concatenate([np.load(tmp_path / f"pairs_v{r}.npy") for r in range(world)])

@@ -26,7 +26,7 @@ def main():
     import oracle as O
     report = {"world": world}
     for fused in (False, True):
-        for kind, log2n in (("uniform", 24), ("zipf", 22), ("unique16", 20), ("all_equal", 18)):
+        for kind, log2n in (("uniform", 24), ("zipf", 22), ("unique16", 20), ("all_equal", 18), ("iota", 20)):
             total = (1 << log2n) + 12345
             per = total // world
             first = rank * per
