@@ -126,6 +126,8 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 31: return launch_modes<31>(pairs, dst, a, s);
     case 32: return launch_modes<32>(pairs, dst, a, s);
     case 33: return launch_modes<33>(pairs, dst, a, s);
+    case 34: return launch_modes<34>(pairs, dst, a, s);
+    case 35: return launch_modes<35>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -18,7 +18,7 @@ struct PassVariant {
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA
 };
-constexpr int kNumVariants = 34;
+constexpr int kNumVariants = 36;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -54,6 +54,8 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 36, 20, 4, 1, 0, 8, 1},   // 31 persistent, four CTAs per SM
     {256, 44, 22, 3, 1, 0, 8, 2},   // 32 = 10 with TMA bulk loads of the tile
     {256, 36, 20, 4, 1, 0, 8, 2},   // 33 TMA, four CTAs per SM
+    {256, 64, 44, 2, 1, 0, 8, 0},   // 34 two CTAs per SM: 64 keys or 44 pairs per thread
+    {256, 64, 36, 2, 1, 0, 8, 0},   // 35
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
