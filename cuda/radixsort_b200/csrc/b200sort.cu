@@ -170,12 +170,13 @@ int run_selftest() {
 
 // Automatic choice: the fastest measured geometry (profiles/r01_sweep_*.jsonl) in atomic-rank mode
 // when the device passed the self test, else the table-rank default.
-constexpr int kAutoVariantW8 = 10;
+constexpr int kAutoVariantW8 = 10;       // keys: 256 threads x 44 keys, three CTAs per SM
+constexpr int kAutoVariantW8Pairs = 35;  // pairs: 256 threads x 36 pairs, two CTAs per SM
 
-int effective_variant(int width) {
+int effective_variant(int width, bool pairs = false) {
     int v = g_params.variant;
     if (v < 0)
-        v = (width == 8) ? kAutoVariantW8
+        v = (width == 8) ? (pairs ? kAutoVariantW8Pairs : kAutoVariantW8)
                          : (width <= 3 ? (g_params.narrow_variant >= 0 ? g_params.narrow_variant : kBallotVariant) : 1);
     if (!variant_available(width, v)) v = 0;
     if (variant_mode(v) == 1 && !run_selftest()) {
@@ -278,7 +279,7 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
     int rc = check_device();
     if (rc) return rc;
 
-    const int variant = effective_variant(pl.width);
+    const int variant = effective_variant(pl.width, pairs);
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, pl.count, pl.width, pairs, true, tile, g_params.portion_tiles);
     if (!temp || ((uintptr_t)temp & 255u)) return fail(B200SORT_ETEMP, "temp storage must be 256-byte aligned");
@@ -592,7 +593,7 @@ uint64_t b200sort_algorithmic_bytes(uint64_t n, int nBits, int pairs) {
     return 4ull * n * (pairs ? 4 * P + 1 : 2 * P + 1);
 }
 
-int b200sort_tile_keys(int pairs) { return tile_keys(effective_variant(8), pairs != 0); }
+int b200sort_tile_keys(int pairs) { return tile_keys(effective_variant(8, pairs != 0), pairs != 0); }
 
 size_t b200sort_temp_bytes(uint64_t n, int nBits, int pairs) {
     return temp_upper_bound(n, nBits, pairs != 0);
@@ -722,7 +723,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
 
-    int variant = effective_variant(bits);
+    int variant = effective_variant(bits, pairs);
     if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant)
         variant = variant_mode(variant) == 1 ? 1 : 0;
     const int tile = tile_keys(variant, pairs);
