@@ -33,6 +33,12 @@ SIGNATURES = {
     "b200sort_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int]),
     "b200sort_shutdown": (C.c_int, []),
+    "b200sort_mgpu_keys_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int), C.c_int]),
+    "b200sort_mgpu_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
+    "b200sort_mgpu_last_stats": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "b200sort_mgpu_shutdown": (C.c_int, []),
     "b200sort_temp_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
     "b200sort_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                 C.c_void_p]),

@@ -27,7 +27,8 @@ from ._lib import RadixSortError
 
 __all__ = [
     "Implementation", "SORT_BY_HOST", "SORT_BY_THRUST", "SORT_BY_DEVICE", "sort", "sortByDevice",
-    "sort_by_device", "sort_pairs_by_device", "Workspace", "sort_keys", "sort_pairs", "histogram",
+    "sort_by_device", "sort_pairs_by_device", "sort_by_devices", "sort_pairs_by_devices", "mgpu_last_stats",
+    "Workspace", "sort_keys", "sort_pairs", "histogram",
     "digit_pass", "exclusive_scan", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
     "tile_keys", "set_param", "get_param", "profile_enable", "profile_read", "launch_count",
     "shutdown",
@@ -81,6 +82,56 @@ def sort_pairs_by_device(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, numBit
     lib = _lib.load()
     _lib.check(lib.b200sort_pairs_host(ki.ctypes.data, vi.ctypes.data, n, ko.ctypes.data, vo.ctypes.data,
                                        numBits, blockSize))
+
+
+def _device_list(devices):
+    import ctypes as C
+    if devices is None:
+        return None, 0
+    if isinstance(devices, int):
+        return None, int(devices)
+    devices = [int(d) for d in devices]
+    return (C.c_int * len(devices))(*devices), len(devices)
+
+
+def sort_by_devices(h_input, n: int, h_output, numBits: int, blockSize: int, devices=None) -> None:
+    """sortByDevice over several GPUs of this node from one process (b200sort_mgpu_keys_host).
+
+    ``devices``: list of CUDA ordinals (repeats allowed: the shards then share that GPU), an
+    int (the first that many devices) or None (every visible device)."""
+    h_input = _host_u32(h_input, "h_input")
+    h_output = _host_u32(h_output, "h_output", writable=True)
+    if n < 0 or n > h_input.size or n > h_output.size:
+        raise ValueError("n exceeds the arrays")
+    arr, count = _device_list(devices)
+    lib = _lib.load()
+    _lib.check(lib.b200sort_mgpu_keys_host(h_input.ctypes.data, n, h_output.ctypes.data, numBits, blockSize,
+                                           arr, count))
+
+
+def sort_pairs_by_devices(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, numBits: int, blockSize: int,
+                          devices=None) -> None:
+    """Stable key/value form of :func:`sort_by_devices` (b200sort_mgpu_pairs_host)."""
+    ki, vi = _host_u32(h_keys_in, "h_keys_in"), _host_u32(h_vals_in, "h_vals_in")
+    ko, vo = _host_u32(h_keys_out, "h_keys_out", True), _host_u32(h_vals_out, "h_vals_out", True)
+    if n < 0 or n > min(ki.size, vi.size, ko.size, vo.size):
+        raise ValueError("n exceeds the arrays")
+    arr, count = _device_list(devices)
+    lib = _lib.load()
+    _lib.check(lib.b200sort_mgpu_pairs_host(ki.ctypes.data, vi.ctypes.data, n, ko.ctypes.data, vo.ctypes.data,
+                                            numBits, blockSize, arr, count))
+
+
+MGPU_STAT_NAMES = ("upload_ms", "histogram_ms", "plan_ms", "partition_ms", "exchange_wait_ms", "local_sort_ms",
+                   "download_ms", "partition_shift", "partition_bits", "imbalance", "devices")
+
+
+def mgpu_last_stats() -> dict:
+    """Device-event figures of the last sort_by_devices / sort_pairs_by_devices call."""
+    import ctypes as C
+    buf = (C.c_double * len(MGPU_STAT_NAMES))()
+    k = _lib.load().b200sort_mgpu_last_stats(buf, len(MGPU_STAT_NAMES))
+    return {name: buf[i] for i, name in enumerate(MGPU_STAT_NAMES[:k])}
 
 
 def sort(in_, n: int, out, implementation=SORT_BY_HOST, numBits: int = 4, blockSize: int = 1) -> None:

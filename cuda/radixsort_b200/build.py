@@ -67,6 +67,9 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     obj = os.path.join(BUILD_DIR, "b200sort.o")
     objs.append(obj)
     jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, "b200sort.cu"), "-o", obj])
+    obj = os.path.join(BUILD_DIR, "mgpu_host.o")
+    objs.append(obj)
+    jobs.append([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "mgpu_host.cu"), "-o", obj])
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
         list(pool.map(lambda c: _run(c, verbose or ptxas_info), jobs))
     _run([nvcc, *ARCH, "-shared", "-Xcompiler", "-pthread", "-o", LIB_PATH, *objs], verbose)

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "../../../include/b200sort.h"
+#include "copy_pool.h"
+#include "internal.h"
 #include "launch.h"
 #include "scan.cuh"
 #include "util_kernels.cuh"
@@ -348,75 +350,6 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
 constexpr size_t kStageChunk = 32u << 20;  // bytes per staging buffer
 constexpr int kStageSlots = 3;
 
-class CopyPool {
-public:
-    void copy(void *dst, const void *src, size_t bytes) {
-        ensure_started();
-        const int parts = (int)workers_.size() + 1;
-        const size_t per = (((bytes + parts - 1) / parts) + 4095) & ~size_t(4095);  // >= 4096 for bytes > 0
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            dst_ = static_cast<char *>(dst);
-            src_ = static_cast<const char *>(src);
-            bytes_ = bytes;
-            per_ = per;
-            pending_ = (int)workers_.size();
-            ++generation_;
-        }
-        cv_.notify_all();
-        run_part(0);  // the caller takes the first slice
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto &t : workers_) t.join();
-    }
-
-private:
-    void ensure_started() {
-        if (started_) return;
-        started_ = true;
-        unsigned hw = std::thread::hardware_concurrency();
-        int n = (int)std::min<unsigned>(hw > 2 ? hw / 2 : 1, 6) - 1;
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { worker(i + 1); });
-    }
-    void run_part(int part) {
-        const size_t off = per_ * (size_t)part;
-        if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
-    }
-    void worker(int part) {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
-                if (stop_) return;
-                seen = generation_;
-            }
-            run_part(part);
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                --pending_;
-            }
-            done_cv_.notify_one();
-        }
-    }
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    std::vector<std::thread> workers_;
-    char *dst_ = nullptr;
-    const char *src_ = nullptr;
-    size_t bytes_ = 0, per_ = 0;
-    int pending_ = 0;
-    uint64_t generation_ = 0;
-    bool stop_ = false, started_ = false;
-};
-
 struct HostCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
@@ -554,6 +487,11 @@ int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
 }
 
 }  // namespace
+
+int set_error(int code, const char *what) { return fail(code, what); }
+int set_cuda_error(cudaError_t e, const char *what) { return fail_cuda(e, what); }
+void set_error_message(const char *message) { g_last_error = message ? message : ""; }
+
 }  // namespace b200sort
 
 using namespace b200sort;
@@ -572,6 +510,7 @@ const char *b200sort_error_string(int code) {
     case B200SORT_EALIAS: return "output aliases input";
     case B200SORT_ENODEVICE: return "no usable sm_100 device";
     case B200SORT_ENOMEM: return "out of device memory";
+    case B200SORT_ENOPEER: return "no peer access between the selected devices";
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "unknown error";
@@ -658,6 +597,7 @@ int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, ui
 }
 
 int b200sort_shutdown(void) {
+    b200sort_mgpu_shutdown();
     std::lock_guard<std::mutex> lock(g_host.mu);
     if (g_host.d_buf) cudaFree(g_host.d_buf);
     g_host.d_buf = nullptr;

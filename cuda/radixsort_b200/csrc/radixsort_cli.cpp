@@ -9,7 +9,8 @@
 // non-zero when a check prints INCORRECT (the reference always returns 0); "by host" is served
 // by std::stable_sort, or -- when the environment variable B200SORT_REF_LIB names a shared
 // object built from the reference's Baseline1.cu -- by the reference's own sortByHost.  Either
-// way it is a checker in this harness only; the library itself has no CPU path.
+// way it is a checker in this harness only; the library itself has no CPU path.  The environment
+// variable B200SORT_GPUS=G shards the device sort over G GPUs of this node (0 = all of them).
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -56,6 +57,10 @@ int main(int argc, char **argv) {
     for (int i = 0; i < n; i++) input[i] = rand();      // unseeded, like the reference
     printf("Block size: %d\n", blockSize);
     printf("Digit width: %d-bit\n", numBits);
+    if (const char *gpus = getenv("B200SORT_GPUS")) {
+        b200compat::device_count() = atoi(gpus);
+        printf("GPUs: %s\n", b200compat::device_count() > 0 ? gpus : "all");
+    }
 
     // "by host": the reference's own function when the caller points at a build of it
     std::string ref = getenv("B200SORT_REF_LIB") ? getenv("B200SORT_REF_LIB") : "";

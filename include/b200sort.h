@@ -41,7 +41,8 @@ enum {
     B200SORT_ETEMP = -3,      /* temp buffer too small or misaligned */
     B200SORT_EALIAS = -4,     /* d_out aliases d_in */
     B200SORT_ENODEVICE = -5,  /* no sm_100 device / CUDA runtime unusable */
-    B200SORT_ENOMEM = -6      /* host-pointer wrapper could not allocate */
+    B200SORT_ENOMEM = -6,     /* host-pointer wrapper could not allocate */
+    B200SORT_ENOPEER = -7     /* multi-GPU entry points: a selected device cannot reach a peer */
 };
 
 /* ---------------------------------------------------------------------------------------
@@ -61,8 +62,42 @@ int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nB
 int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n,
                         uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits, int blockSize);
 
-/* Frees the cached device/pinned buffers of the host-pointer entry points. */
+/* Frees the cached device/pinned buffers of the host-pointer entry points (single- and
+ * multi-GPU). */
 int b200sort_shutdown(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Single-process multi-GPU host-pointer sort: the same contract as b200sort_keys_host /
+ * sortByDevice (SourceCode/Parallel7.cu:530), with the array sharded over `num_devices`
+ * GPUs of one node driven from the calling thread.  The reference has no multi-GPU path;
+ * this is the form its single-process main() (SourceCode/Parallel7.cu:696-775) could call.
+ *   shard g = elements [g*n/G, (g+1)*n/G)  ->  H2D over each GPU's own PCIe link
+ *   -> digit histogram of the partition byte (b200sort_histogram) -> splitters on bin edges
+ *   -> one stable digit pass whose per-bin destinations are peer addresses in the owners'
+ *      receive buffers (b200sort_digit_pass with d_bin_dst: partition fused with the NVLink
+ *      exchange) -> local sort of each received range (b200sort_keys / b200sort_pairs)
+ *   -> D2H into h_out at the range's global offset.
+ * devices: `num_devices` CUDA ordinals (an ordinal may repeat: the shards then share that
+ * GPU, which exercises the whole path on a one-GPU box); NULL = 0 .. num_devices-1;
+ * num_devices <= 0 = every visible device.  Needs peer access between distinct devices
+ * (B200SORT_ENOPEER otherwise).  n may exceed 2^32-1 as long as every shard and every
+ * received range stays below 2^32 keys.  Blocking; buffers cached until
+ * b200sort_mgpu_shutdown() / b200sort_shutdown().  The multi-process form of the same
+ * algorithm (one rank per GPU over torch.distributed) is cuda/radixsort_b200/mgpu.py. */
+int b200sort_mgpu_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nBits,
+                            int blockSize, const int *devices, int num_devices);
+int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n,
+                             uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits,
+                             int blockSize, const int *devices, int num_devices);
+
+/* Figures of the last b200sort_mgpu_*_host call (device-event times, maximum over the
+ * devices): out[0..6] = milliseconds of upload, histogram, plan (host: splitters), partition
+ * kernel, wait for the peers' partitions, local sort, download; out[7] = partition shift,
+ * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices.
+ * Returns the number of values written (<= capacity). */
+enum { B200SORT_MGPU_STATS = 11 };
+int b200sort_mgpu_last_stats(double *out, int capacity);
+int b200sort_mgpu_shutdown(void);
 
 /* ---------------------------------------------------------------------------------------
  * Device-resident entry points: the per-digit loop of sortByDevice

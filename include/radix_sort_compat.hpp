@@ -13,6 +13,9 @@
 //             int numBits = 4, int blockSize = 1);             (:650-661)
 //   -- (north star spelling)                                  void sort(in, n, out, bool useDevice,
 //                                                                       int blockSize)
+//   -- (no multi-GPU path)                                    b200compat::device_count() = G makes
+//                                                               sortByDevice shard over G GPUs
+//                                                               (b200sort_mgpu_keys_host)
 //
 // Error behaviour follows the reference's CHECK macro (SourceCode/common/common.h:6-16): on
 // failure print "Error: file:line, code: N, reason: ..." to stderr and exit(EXIT_FAILURE).
@@ -52,6 +55,13 @@ inline int &default_nbits() {
     return nbits;
 }
 
+// Number of GPUs sortByDevice() shards the array over (1 = the single-GPU entry point;
+// 0 = every visible device).  The reference is single-GPU; this is the one-line opt-in.
+inline int &device_count() {
+    static int count = 1;
+    return count;
+}
+
 inline void check(int rc, const char *file, int line) {
     if (rc != B200SORT_OK) {
         std::fprintf(stderr, "Error: %s:%d, ", file, line);
@@ -66,7 +76,12 @@ inline void check(int rc, const char *file, int line) {
 
 // Drop-in for the reference's sortByDevice (SourceCode/Parallel7.cu:530).
 inline void sortByDevice(const uint32_t *h_input, int n, uint32_t *h_output, int numBits, int blockSize) {
-    B200_CHECK(b200sort_keys_host(h_input, n < 0 ? 0 : (uint64_t)n, h_output, numBits, blockSize));
+    const uint64_t count = n < 0 ? 0 : (uint64_t)n;
+    if (b200compat::device_count() == 1)
+        B200_CHECK(b200sort_keys_host(h_input, count, h_output, numBits, blockSize));
+    else
+        B200_CHECK(b200sort_mgpu_keys_host(h_input, count, h_output, numBits, blockSize, nullptr,
+                                           b200compat::device_count()));
 }
 
 // Drop-in for the reference's sort() (SourceCode/Parallel7.cu:641-662), including its output.

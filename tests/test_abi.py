@@ -20,7 +20,8 @@ def declared_symbols():
 def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for must in ("b200sort_keys_host", "b200sort_pairs_host", "b200sort_keys", "b200sort_pairs",
-                 "b200sort_temp_bytes", "b200sort_histogram", "b200sort_digit_pass"):
+                 "b200sort_temp_bytes", "b200sort_histogram", "b200sort_digit_pass",
+                 "b200sort_mgpu_keys_host", "b200sort_mgpu_pairs_host"):
         assert must in syms
 
 
@@ -82,6 +83,11 @@ def test_argument_errors_without_touching_the_gpu(rs):
     assert lib.b200sort_keys_host(None, 16, o.ctypes.data, 8, 512) == -1
     assert lib.b200sort_keys_host(a.ctypes.data, 0, o.ctypes.data, 8, 512) == 0        # n == 0 no-op
     assert lib.b200sort_keys(None, 0, None, None, 0, 8, None) == 0
+    # multi-GPU host entry points validate before they look for devices
+    assert lib.b200sort_mgpu_keys_host(a.ctypes.data, 16, o.ctypes.data, 0, 512, None, 2) == -1
+    assert lib.b200sort_mgpu_keys_host(a.ctypes.data, 16, o.ctypes.data, 8, 0, None, 2) == -1
+    assert lib.b200sort_mgpu_last_stats(None, 0) == 0
+    assert lib.b200sort_mgpu_shutdown() == 0
     assert lib.b200sort_set_param(b"variant", 99) == -1
     assert lib.b200sort_set_param(b"variant", -1) == 0     # automatic choice
     assert lib.b200sort_set_param(b"no_such_param", 1) == -1

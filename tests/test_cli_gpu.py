@@ -43,3 +43,10 @@ def test_cli_rejects_bad_digit_width_like_check(rs):
     r = run_cli([512, 0, 100])
     assert r.returncode != 0
     assert "Error:" in r.stderr and "code:" in r.stderr and "reason:" in r.stderr    # CHECK format, common.h:6-16
+
+
+def test_cli_sharded_over_all_gpus(rs):
+    # B200SORT_GPUS: sortByDevice goes through b200sort_mgpu_keys_host (every visible device)
+    r = run_cli([512, 8, (1 << 22) + 3], {"B200SORT_GPUS": "0"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GPUs: all" in r.stdout and r.stdout.count("CORRECT :)") == 2

@@ -1,0 +1,117 @@
+"""GPU parity of the single-process multi-GPU host entry points (b200sort_mgpu_*_host) against
+the oracle.  Shards may share one GPU (a repeated ordinal), so the whole partition / exchange /
+local-sort path runs on a one-GPU box as well; with two or more GPUs the same cases also run
+across real peers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def device_sets():
+    import torch
+    sets = [[0], [0, 0], [0, 0, 0], [0, 0, 0, 0]]
+    g = torch.cuda.device_count()
+    if g >= 2:
+        sets.append(list(range(2)))
+    if g >= 4:
+        sets.append(list(range(4)))
+    if g >= 3:
+        sets.append(list(range(g)))
+    return sets
+
+
+def run(rs, keys, nbits, devices):
+    out = np.zeros_like(keys)
+    rs.sort_by_devices(keys, keys.size, out, nbits, 512, devices)
+    return out
+
+
+def test_kat_debug_and_default_config(rs, oracle):
+    k = oracle.glibc_rand_keys(513, 0xFF)
+    for devs in device_sets():
+        assert oracle.fnv1a64(run(rs, k, 4, devs)) == 0x714658018BFDCBDC
+    k = oracle.glibc_rand_keys((1 << 24) + 1)
+    for devs in device_sets()[1:]:
+        out = run(rs, k, 8, devs)
+        assert oracle.fnv1a64(out) == 0xE354BCFF33580302
+        st = rs.mgpu_last_stats()
+        assert st["devices"] == len(devs) and st["imbalance"] < 1.1
+
+
+@pytest.mark.parametrize("kind", ["uniform", "zipf", "unique16", "all_equal", "sorted", "reversed", "iota"])
+def test_distributions(rs, oracle, kind):
+    n = (1 << 20) + 77
+    k = oracle.generate(kind, n)
+    want = oracle.sort_keys(k, 8)
+    for devs in device_sets():
+        assert np.array_equal(run(rs, k, 8, devs), want), (kind, devs)
+
+
+def test_uniform_keys_take_the_narrow_partition(rs, oracle):
+    k = oracle.generate("uniform", 1 << 21)
+    out = run(rs, k, 8, [0, 0, 0, 0])
+    assert np.array_equal(out, oracle.sort_keys(k, 8))
+    st = rs.mgpu_last_stats()
+    assert st["partition_bits"] == 2 and st["partition_shift"] == 30 and st["imbalance"] < 1.05
+    run(rs, k, 8, [0, 0, 0])
+    assert rs.mgpu_last_stats()["partition_bits"] == 8
+
+
+def test_edge_sizes_and_digit_widths(rs, oracle):
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 2, 3, 5, 31, 32, 33, 1000, 11264, 11265, (1 << 18) + 1):
+        k = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        for devs in ([0, 0], [0, 0, 0]):
+            assert np.array_equal(run(rs, k, 8, devs), np.sort(k)), (n, devs)
+    k = rng.integers(0, 1 << 32, 300001, dtype=np.uint64).astype(np.uint32)
+    for nbits in (1, 3, 4, 5, 7, 11, 16):
+        assert np.array_equal(run(rs, k, nbits, [0, 0]), oracle.sort_keys(k, nbits)), nbits
+
+
+def test_keys_sharing_their_high_bytes(rs, oracle):
+    rng = np.random.default_rng(12)
+    n = 200003
+    for low_bits in (24, 16, 8, 3):
+        k = (np.uint32(0xA5C3F00F) & np.uint32((0xFFFFFFFF << low_bits) & 0xFFFFFFFF)) | \
+            rng.integers(0, 1 << low_bits, n, dtype=np.uint64).astype(np.uint32)
+        out = run(rs, k, 8, [0, 0, 0, 0])
+        assert np.array_equal(out, np.sort(k)), low_bits
+        assert rs.mgpu_last_stats()["partition_shift"] < 32 - 8 or low_bits > 24
+
+
+def test_pairs_are_stable_across_shards(rs, oracle):
+    rng = np.random.default_rng(13)
+    n = (1 << 19) + 5
+    for hi in (1 << 32, 1 << 10, 3):
+        k = rng.integers(0, hi, n, dtype=np.uint64).astype(np.uint32)
+        v = np.arange(n, dtype=np.uint32)
+        wk, wv = oracle.sort_pairs(k, v, 8)
+        for devs in device_sets():
+            ok, ov = np.zeros_like(k), np.zeros_like(v)
+            rs.sort_pairs_by_devices(k, v, n, ok, ov, 8, 512, devs)
+            assert np.array_equal(ok, wk) and np.array_equal(ov, wv), (hi, devs)
+
+
+def test_pageable_and_pinned_hosts_and_in_place(rs, oracle):
+    import torch
+    n = (1 << 24) + 4099          # several 16 MiB staging chunks per shard, ragged tail
+    k = oracle.generate("uniform", n)
+    want = np.sort(k)
+    for devs in ([0, 0], [0, 0, 0]):
+        assert np.array_equal(run(rs, k, 8, devs), want)
+    pin_in = torch.empty(n, dtype=torch.int32).pin_memory()
+    pin_out = torch.empty(n, dtype=torch.int32).pin_memory()
+    pin_in.numpy().view(np.uint32)[:] = k
+    rs.sort_by_devices(pin_in.numpy().view(np.uint32), n, pin_out.numpy().view(np.uint32), 8, 512, [0, 0])
+    assert np.array_equal(pin_out.numpy().view(np.uint32), want)
+    buf = k.copy()
+    rs.sort_by_devices(buf, n, buf, 8, 512, [0, 0])   # h_out == h_in, as the reference tolerates
+    assert np.array_equal(buf, want)
+
+
+def test_bad_devices_are_refused(rs):
+    k = np.arange(8, dtype=np.uint32)
+    with pytest.raises(rs.RadixSortError):
+        rs.sort_by_devices(k, 8, k.copy(), 8, 512, [0, 4096])
+    rs.sort_by_devices(k, 8, k.copy(), 8, 512, None)   # every visible device
