@@ -83,6 +83,7 @@ struct Shard {
     // per call
     uint64_t first = 0, count = 0;  // shard of the input
     uint64_t recv = 0, out_first = 0;
+    const uint32_t *range_k = nullptr, *range_v = nullptr;  // what the local sort reads
     uint32_t *sorted_k = nullptr, *sorted_v = nullptr;
 };
 
@@ -280,6 +281,140 @@ int mark(Shard &s, int which) {
     return 0;
 }
 
+// Histogram of the partition digit on every shard, splitters, then one digit pass per shard that
+// writes each bin into its owner's receive buffer.  On return every stream has waited for all
+// partitions and the shards know their received range.
+int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool pairs, int &part_shift_out,
+                           int &part_bits_out, uint64_t &max_recv_out) {
+    const int G = (int)sh.size();
+    // ---- partition digit: the highest byte in which the keys differ -----------------------------
+    std::vector<uint64_t> counts((size_t)G * kPartBins);
+    std::vector<uint64_t> global(kPartBins);
+    int shift = 32 - kPartBits;
+    for (;;) {
+        for (auto &s : sh) {
+            CU(cudaSetDevice(s.dev));
+            uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);
+            RC(b200sort_histogram(static_cast<const uint32_t *>(s.in_k.p), s.count, shift, kPartBits, d_hist,
+                                  s.temp.p, s.temp.bytes, s.stream));
+            CU(cudaMemcpyAsync(s.h_counts, d_hist, kPartBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaEventRecord(s.ev[EV_HIST], s.stream));
+        }
+        RC(sync_all(sh));
+        std::fill(global.begin(), global.end(), 0);
+        for (int i = 0; i < G; ++i)
+            for (int b = 0; b < kPartBins; ++b) {
+                counts[(size_t)i * kPartBins + b] = sh[i].h_counts[b];
+                global[b] += sh[i].h_counts[b];
+            }
+        const bool one_bin = *std::max_element(global.begin(), global.end()) == n;
+        if (!one_bin || shift == 0) break;
+        shift -= kPartBits;  // every key shares this byte: partition on the next one
+    }
+
+    // ---- plan ----------------------------------------------------------------------------------
+    std::vector<int> owner(kPartBins);
+    choose_owner(global.data(), kPartBins, G, owner.data());
+    std::vector<uint64_t> matrix((size_t)G * G, 0);  // [src][dst]
+    for (int i = 0; i < G; ++i)
+        for (int b = 0; b < kPartBins; ++b) matrix[(size_t)i * G + owner[b]] += counts[(size_t)i * kPartBins + b];
+    uint64_t max_recv = 0, running_out = 0;
+    for (int d = 0; d < G; ++d) {
+        uint64_t tot = 0;
+        for (int i = 0; i < G; ++i) tot += matrix[(size_t)i * G + d];
+        if (tot > 0xFFFFFFFFull) return set_error(B200SORT_ETOOBIG, "received range");
+        sh[d].recv = tot;
+        sh[d].out_first = running_out;
+        running_out += tot;
+        max_recv = std::max(max_recv, tot);
+    }
+    // Splitters on the top log2(G) bits (uniform keys, G a power of two): partition with a
+    // log2(G)-bit digit -- G bins instead of 256, long runs per (tile, destination).
+    int lg = 0;
+    while ((1 << (lg + 1)) <= G) ++lg;
+    bool narrow = G > 1 && (1 << lg) == G && lg <= kPartBits;
+    for (int b = 0; narrow && b < kPartBins; ++b) narrow = owner[b] == (b >> (kPartBits - lg));
+    const int part_bits = narrow ? lg : kPartBits;
+    const int part_shift = narrow ? shift + kPartBits - lg : shift;
+    const int part_bins = 1 << part_bits;
+
+    for (int d = 0; d < G; ++d) {
+        Shard &s = sh[d];
+        CU(cudaSetDevice(s.dev));
+        const size_t bytes = align_up(std::max<uint64_t>(s.recv, 1) * 4, 256);
+        RC(s.recv_k.ensure(bytes));
+        if (pairs) RC(s.recv_v.ensure(bytes));
+        s.range_k = static_cast<const uint32_t *>(s.recv_k.p);
+        s.range_v = static_cast<const uint32_t *>(s.recv_v.p);
+        if (bytes <= s.in_k.bytes) {  // the shard's input buffer is free once every partition is done
+            s.sorted_k = static_cast<uint32_t *>(s.in_k.p);
+            s.sorted_v = static_cast<uint32_t *>(s.in_v.p);
+        } else {
+            RC(s.out_k.ensure(bytes));
+            if (pairs) RC(s.out_v.ensure(bytes));
+            s.sorted_k = static_cast<uint32_t *>(s.out_k.p);
+            s.sorted_v = static_cast<uint32_t *>(s.out_v.p);
+        }
+        const size_t t = std::max(b200sort_temp_bytes(s.recv, nbits, pairs), s.temp.bytes);
+        if (t > s.temp.bytes) RC(s.temp.ensure(align_up(t, 256)));
+    }
+
+    // ---- partition fused with the exchange -------------------------------------------------------
+    std::vector<uint64_t> src_base(G, 0);  // keys of lower source ranks already placed in each owner's range
+    for (int i = 0; i < G; ++i) {
+        Shard &s = sh[i];
+        std::vector<uint64_t> at(src_base);
+        for (int b = 0; b < part_bins; ++b) {
+            const int o = narrow ? b : owner[b];
+            const uint64_t cnt = narrow ? matrix[(size_t)i * G + b] : counts[(size_t)i * kPartBins + b];
+            s.h_bin_dst[b] = reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_k.p) + at[o]);
+            s.h_bin_dst[part_bins + b] = pairs ? reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_v.p) + at[o]) : 0;
+            at[o] += cnt;
+        }
+        for (int d = 0; d < G; ++d) src_base[d] += matrix[(size_t)i * G + d];
+        CU(cudaSetDevice(s.dev));
+        uint64_t *d_bin_dst = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 2048);
+        CU(cudaMemcpyAsync(d_bin_dst, s.h_bin_dst, (size_t)2 * part_bins * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaEventRecord(s.ev[EV_PLANNED], s.stream));
+        if (s.count)
+            RC(b200sort_digit_pass(static_cast<const uint32_t *>(s.in_k.p),
+                                   pairs ? static_cast<const uint32_t *>(s.in_v.p) : nullptr, s.count, nullptr, nullptr,
+                                   part_shift, part_bits, d_bin_dst, s.temp.p, s.temp.bytes, s.stream));
+        CU(cudaEventRecord(s.ev[EV_PARTITIONED], s.stream));
+    }
+    for (int i = 0; i < G; ++i) {
+        CU(cudaSetDevice(sh[i].dev));
+        for (int j = 0; j < G; ++j)
+            if (j != i) CU(cudaStreamWaitEvent(sh[i].stream, sh[j].ev[EV_PARTITIONED], 0));
+        CU(cudaEventRecord(sh[i].ev[EV_EXCHANGED], sh[i].stream));
+    }
+
+    part_shift_out = part_shift;
+    part_bits_out = part_bits;
+    max_recv_out = max_recv;
+    return 0;
+}
+
+// One shard: nothing to partition, the uploaded array is sorted as it is.
+int single_shard(Shard &s, int nbits, bool pairs, uint64_t &max_recv_out) {
+    CU(cudaSetDevice(s.dev));
+    const size_t bytes = align_up(std::max<uint64_t>(s.count, 1) * 4, 256);
+    RC(s.out_k.ensure(bytes));
+    if (pairs) RC(s.out_v.ensure(bytes));
+    const size_t t = b200sort_temp_bytes(s.count, nbits, pairs);
+    if (t > s.temp.bytes) RC(s.temp.ensure(align_up(t, 256)));
+    // the "received range" is the input buffer itself
+    s.range_k = static_cast<const uint32_t *>(s.in_k.p);
+    s.range_v = static_cast<const uint32_t *>(s.in_v.p);
+    s.recv = s.count;
+    s.out_first = 0;
+    s.sorted_k = static_cast<uint32_t *>(s.out_k.p);
+    s.sorted_v = static_cast<uint32_t *>(s.out_v.p);
+    for (int e : {EV_HIST, EV_PLANNED, EV_PARTITIONED, EV_EXCHANGED}) CU(cudaEventRecord(s.ev[e], s.stream));
+    max_recv_out = s.count;
+    return 0;
+}
+
 int sort_mgpu(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t *hk_out, uint32_t *hv_out,
               int nbits, int block_size, const int *devices, int num_devices, bool pairs) {
     if (nbits < 1 || nbits > 16) return set_error(B200SORT_EINVAL, "nBits must be in 1..16");
@@ -351,115 +486,20 @@ int sort_mgpu(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
     if (pairs) RC(upload_all(sh, hv_in, true));
     for (auto &s : sh) RC(mark(s, EV_UPLOADED));
 
-    // ---- partition digit: the highest byte in which the keys differ -----------------------------
-    std::vector<uint64_t> counts((size_t)G * kPartBins);
-    std::vector<uint64_t> global(kPartBins);
-    int shift = 32 - kPartBits;
-    for (;;) {
-        for (auto &s : sh) {
-            CU(cudaSetDevice(s.dev));
-            uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);
-            RC(b200sort_histogram(static_cast<const uint32_t *>(s.in_k.p), s.count, shift, kPartBits, d_hist,
-                                  s.temp.p, s.temp.bytes, s.stream));
-            CU(cudaMemcpyAsync(s.h_counts, d_hist, kPartBins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaEventRecord(s.ev[EV_HIST], s.stream));
-        }
-        RC(sync_all(sh));
-        std::fill(global.begin(), global.end(), 0);
-        for (int i = 0; i < G; ++i)
-            for (int b = 0; b < kPartBins; ++b) {
-                counts[(size_t)i * kPartBins + b] = sh[i].h_counts[b];
-                global[b] += sh[i].h_counts[b];
-            }
-        const bool one_bin = *std::max_element(global.begin(), global.end()) == n;
-        if (!one_bin || shift == 0) break;
-        shift -= kPartBits;  // every key shares this byte: partition on the next one
-    }
-
-    // ---- plan ----------------------------------------------------------------------------------
-    std::vector<int> owner(kPartBins);
-    choose_owner(global.data(), kPartBins, G, owner.data());
-    std::vector<uint64_t> matrix((size_t)G * G, 0);  // [src][dst]
-    for (int i = 0; i < G; ++i)
-        for (int b = 0; b < kPartBins; ++b) matrix[(size_t)i * G + owner[b]] += counts[(size_t)i * kPartBins + b];
-    uint64_t max_recv = 0, running_out = 0;
-    for (int d = 0; d < G; ++d) {
-        uint64_t tot = 0;
-        for (int i = 0; i < G; ++i) tot += matrix[(size_t)i * G + d];
-        if (tot > 0xFFFFFFFFull) return set_error(B200SORT_ETOOBIG, "received range");
-        sh[d].recv = tot;
-        sh[d].out_first = running_out;
-        running_out += tot;
-        max_recv = std::max(max_recv, tot);
-    }
-    // Splitters on the top log2(G) bits (uniform keys, G a power of two): partition with a
-    // log2(G)-bit digit -- G bins instead of 256, long runs per (tile, destination).
-    int lg = 0;
-    while ((1 << (lg + 1)) <= G) ++lg;
-    bool narrow = G > 1 && (1 << lg) == G && lg <= kPartBits;
-    for (int b = 0; narrow && b < kPartBins; ++b) narrow = owner[b] == (b >> (kPartBits - lg));
-    const int part_bits = narrow ? lg : kPartBits;
-    const int part_shift = narrow ? shift + kPartBits - lg : shift;
-    const int part_bins = 1 << part_bits;
-
-    for (int d = 0; d < G; ++d) {
-        Shard &s = sh[d];
-        CU(cudaSetDevice(s.dev));
-        const size_t bytes = align_up(std::max<uint64_t>(s.recv, 1) * 4, 256);
-        RC(s.recv_k.ensure(bytes));
-        if (pairs) RC(s.recv_v.ensure(bytes));
-        if (bytes <= s.in_k.bytes) {  // the shard's input buffer is free once every partition is done
-            s.sorted_k = static_cast<uint32_t *>(s.in_k.p);
-            s.sorted_v = static_cast<uint32_t *>(s.in_v.p);
-        } else {
-            RC(s.out_k.ensure(bytes));
-            if (pairs) RC(s.out_v.ensure(bytes));
-            s.sorted_k = static_cast<uint32_t *>(s.out_k.p);
-            s.sorted_v = static_cast<uint32_t *>(s.out_v.p);
-        }
-        const size_t t = std::max(b200sort_temp_bytes(s.recv, nbits, pairs), s.temp.bytes);
-        if (t > s.temp.bytes) RC(s.temp.ensure(align_up(t, 256)));
-    }
-
-    // ---- partition fused with the exchange -------------------------------------------------------
-    std::vector<uint64_t> src_base(G, 0);  // keys of lower source ranks already placed in each owner's range
-    for (int i = 0; i < G; ++i) {
-        Shard &s = sh[i];
-        std::vector<uint64_t> at(src_base);
-        for (int b = 0; b < part_bins; ++b) {
-            const int o = narrow ? b : owner[b];
-            const uint64_t cnt = narrow ? matrix[(size_t)i * G + b] : counts[(size_t)i * kPartBins + b];
-            s.h_bin_dst[b] = reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_k.p) + at[o]);
-            s.h_bin_dst[part_bins + b] = pairs ? reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_v.p) + at[o]) : 0;
-            at[o] += cnt;
-        }
-        for (int d = 0; d < G; ++d) src_base[d] += matrix[(size_t)i * G + d];
-        CU(cudaSetDevice(s.dev));
-        uint64_t *d_bin_dst = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 2048);
-        CU(cudaMemcpyAsync(d_bin_dst, s.h_bin_dst, (size_t)2 * part_bins * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-        CU(cudaEventRecord(s.ev[EV_PLANNED], s.stream));
-        if (s.count)
-            RC(b200sort_digit_pass(static_cast<const uint32_t *>(s.in_k.p),
-                                   pairs ? static_cast<const uint32_t *>(s.in_v.p) : nullptr, s.count, nullptr, nullptr,
-                                   part_shift, part_bits, d_bin_dst, s.temp.p, s.temp.bytes, s.stream));
-        CU(cudaEventRecord(s.ev[EV_PARTITIONED], s.stream));
-    }
-    for (int i = 0; i < G; ++i) {
-        CU(cudaSetDevice(sh[i].dev));
-        for (int j = 0; j < G; ++j)
-            if (j != i) CU(cudaStreamWaitEvent(sh[i].stream, sh[j].ev[EV_PARTITIONED], 0));
-        CU(cudaEventRecord(sh[i].ev[EV_EXCHANGED], sh[i].stream));
-    }
+    int part_shift = 0, part_bits = 0;
+    uint64_t max_recv = 0;
+    if (G > 1) RC(partition_and_exchange(sh, n, nbits, pairs, part_shift, part_bits, max_recv));
+    else RC(single_shard(sh[0], nbits, pairs, max_recv));
 
     // ---- local sorts, download -------------------------------------------------------------------
     for (auto &s : sh) {
         CU(cudaSetDevice(s.dev));
         if (s.recv) {
             if (pairs)
-                RC(b200sort_pairs(static_cast<const uint32_t *>(s.recv_k.p), static_cast<const uint32_t *>(s.recv_v.p), s.recv,
+                RC(b200sort_pairs(s.range_k, s.range_v, s.recv,
                                   s.sorted_k, s.sorted_v, s.temp.p, s.temp.bytes, nbits, s.stream));
             else
-                RC(b200sort_keys(static_cast<const uint32_t *>(s.recv_k.p), s.recv, s.sorted_k, s.temp.p, s.temp.bytes,
+                RC(b200sort_keys(s.range_k, s.recv, s.sorted_k, s.temp.p, s.temp.bytes,
                                  nbits, s.stream));
         }
         CU(cudaEventRecord(s.ev[EV_SORTED], s.stream));
