@@ -90,9 +90,10 @@ int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_i
                              uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits,
                              int blockSize, const int *devices, int num_devices);
 
-/* Figures of the last b200sort_mgpu_*_host call (device-event times, maximum over the
- * devices): out[0..6] = milliseconds of upload, histogram, plan (host: splitters), partition
- * kernel, wait for the peers' partitions, local sort, download; out[7] = partition shift,
+/* Figures of the last b200sort_mgpu_*_host call: out[0..6] = milliseconds of upload,
+ * histogram, plan (host clock: splitters, receive buffers), partition kernel, wait for the
+ * peers' partitions, local sort, download -- device-event times, each the maximum over the
+ * devices, so they need not add up to the call's wall time; out[7] = partition shift,
  * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices.
  * Returns the number of values written (<= capacity). */
 enum { B200SORT_MGPU_STATS = 11 };
