@@ -37,10 +37,10 @@ struct Params {
 
 // RANK_ATOMIC variants are only used after the on-device self test has passed.
 // -1 = not run yet, 0 = failed (fall back to the table-rank twin), 1 = passed.
-int g_atomic_rank_ok = -1;
+std::atomic<int> g_atomic_rank_ok{-1};
 
-int g_num_sms = 0;
-int g_device_checked = -1000;
+std::atomic<int> g_num_sms{0};
+std::atomic<int> g_device_checked{-1000};
 
 int fail(int code, const char *what) {
     g_last_error = std::string(what) + ": " + b200sort_error_string(code);

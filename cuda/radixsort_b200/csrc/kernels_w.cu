@@ -1,6 +1,7 @@
 // kernels_w.cu -- instantiates the histogram and digit-pass kernels for ONE digit width.
 // Compiled eight times (-DB200_W=1 .. 8) so the widths build in parallel.
 #include <algorithm>
+#include <atomic>
 
 #include "hist.cuh"
 #include "launch.h"
@@ -23,20 +24,20 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int TB = g.table_bits;
     using TR = PassTraits<W, g.threads, ITEMS, g.mode, TB, PAIRS, DST>;
     auto kernel = onesweep_pass_kernel<W, g.threads, ITEMS, g.min_ctas, g.mode, TB, g.lb_batch, (g.persist == 1), (g.persist == 2), PAIRS, DST>;
-    static uint64_t configured = 0;  // one bit per device: the attribute is per device
+    static std::atomic<uint64_t> configured{0};  // one bit per device: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1u)) {
+    if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)TR::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured |= 1ull << (dev & 63);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
     unsigned grid = a.num_tiles;
     if (g.persist == 1) {
         // every CTA of a persistent launch must be resident: the look-back spins on tiles that
         // belong to other CTAs of the same launch
-        static int resident[64] = {};
+        static std::atomic<int> resident[64] = {};
         if (resident[dev & 63] == 0) {
             int per_sm = 0, sms = 0;
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, g.threads, TR::SMEM_BYTES);
@@ -65,7 +66,7 @@ template <int P_CT>
 cudaError_t launch_hist_impl(const HistArgs &a, int passes, int grid, cudaStream_t s) {
     auto kernel = hist_kernel<W, P_CT>;
     const size_t smem = hist_smem_bytes(passes, W);
-    static size_t configured[64] = {};  // per device
+    static std::atomic<size_t> configured[64] = {};  // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {

@@ -364,3 +364,33 @@ def test_reference_parallel7_agrees(rs, oracle):
     theirs = oracle.ref_sort_by_device(k, 8, 512)
     assert np.array_equal(mine, theirs)
     assert np.array_equal(mine, oracle.sort_keys(k, 8))
+
+
+def test_device_entry_points_are_reentrant_across_host_threads_and_streams(rs, oracle):
+    # include/b200sort.h: the device-pointer entry points may run concurrently given distinct
+    # temp buffers and streams (the reference, with its function-static buffers, cannot)
+    import threading
+    import torch
+    rng = np.random.default_rng(21)
+    jobs = []
+    for t in range(4):
+        k = rng.integers(0, 1 << 32, (1 << 20) + 1000 * t + 7, dtype=np.uint64).astype(np.uint32)
+        jobs.append({"keys": k, "dev": to_dev(k), "ws": rs.Workspace("cuda"), "stream": torch.cuda.Stream(),
+                     "nbits": (8, 4, 8, 5)[t], "out": []})
+    torch.cuda.synchronize()
+
+    def work(job):
+        with torch.cuda.stream(job["stream"]):
+            for _ in range(6):
+                job["out"].append(rs.sort_keys(job["dev"], job["nbits"], workspace=job["ws"]))
+        job["stream"].synchronize()
+
+    threads = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for j in jobs:
+        want = np.sort(j["keys"])
+        for o in j["out"]:
+            assert np.array_equal(to_host(o), want)
