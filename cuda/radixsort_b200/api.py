@@ -29,7 +29,7 @@ __all__ = [
     "Implementation", "SORT_BY_HOST", "SORT_BY_THRUST", "SORT_BY_DEVICE", "sort", "sortByDevice",
     "sort_by_device", "sort_pairs_by_device", "sort_by_devices", "sort_pairs_by_devices", "mgpu_last_stats",
     "Workspace", "sort_keys", "sort_pairs", "histogram",
-    "digit_pass", "exclusive_scan", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
+    "digit_pass", "route", "exclusive_scan", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
     "tile_keys", "set_param", "get_param", "profile_enable", "profile_read", "launch_count",
     "shutdown",
 ]
@@ -291,6 +291,22 @@ def digit_pass(keys, shift: int, bits: int, vals=None, out_keys=None, out_vals=N
                                        n, okp, ovp, shift, bits, dstp, tmp.data_ptr(), tmp.numel(),
                                        _stream_ptr(stream)))
     return (out_keys, out_vals) if vals is not None else out_keys
+
+
+def route(keys, thresholds, out=None, stream=None):
+    """out[i] = number of thresholds <= keys[i] (unsigned): b200sort_route.
+
+    ``thresholds``: non-decreasing integers in [0, 2^32] (a sequence or a CUDA int64 tensor)."""
+    torch = _torch()
+    if not torch.is_tensor(thresholds):
+        thresholds = torch.tensor([int(t) for t in thresholds], dtype=torch.int64, device=keys.device)
+    if thresholds.dtype != torch.int64 or not thresholds.is_cuda:
+        raise TypeError("thresholds must be a CUDA int64 tensor")
+    out = torch.empty_like(keys) if out is None else out
+    _lib.check(_lib.load().b200sort_route(_dev_ptr(keys, "keys"), keys.numel(),
+                                          thresholds.data_ptr() if thresholds.numel() else None,
+                                          thresholds.numel(), _dev_ptr(out, "out"), _stream_ptr(stream)))
+    return out
 
 
 def exclusive_scan(x, out=None, workspace: Workspace | None = None, stream=None):

@@ -77,6 +77,33 @@ __global__ void __launch_bounds__(256) verify_kernel(const uint32_t *__restrict_
     }
 }
 
+// route[i] = #{j < count : thresholds[j] <= key[i]} for non-decreasing 64-bit thresholds in
+// [0, 2^32]: the destination shard of a key under value splitters (multi-GPU, skewed keys).
+// The result is then used as the KEY of a digit pass that carries the real keys as values.
+constexpr int kMaxRouteThresholds = 255;
+__global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__ keys, uint64_t n,
+                                                    const uint64_t *__restrict__ thresholds, int count,
+                                                    uint32_t *__restrict__ route) {
+    __shared__ uint64_t s_t[kMaxRouteThresholds + 1];
+    for (int j = threadIdx.x; j < count; j += blockDim.x) s_t[j] = thresholds[j];
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[i];
+        uint32_t r = 0;
+        if (count <= 8) {
+            for (int j = 0; j < count; ++j) r += (s_t[j] <= k) ? 1u : 0u;
+        } else {  // upper bound by bisection
+            int lo = 0, hi = count;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_t[mid] <= k) lo = mid + 1; else hi = mid;
+            }
+            r = (uint32_t)lo;
+        }
+        route[i] = r;
+    }
+}
+
 // Probe for the fused exchange: copies n uint32 from src to dst (dst may be peer memory) with
 // 4-byte (vec = 1) or 16-byte (vec = 4) stores per lane, `chunk` consecutive keys per warp visit
 // (chunk = 32 imitates the digit-pass write-out: one 128-byte run per warp store).

@@ -55,7 +55,7 @@ def choose_owner(global_hist: np.ndarray, world: int) -> np.ndarray:
     return owner
 
 
-def plan_exchange(counts_all: np.ndarray, rank: int):
+def plan_exchange(counts_all: np.ndarray, rank: int, owner=None):
     """counts_all[src][bin] -> everything a rank needs for the exchange.
 
     Returns dict with owner[bin], send_counts[dst], recv_counts[src], recv_offsets[src] (where
@@ -63,7 +63,7 @@ def plan_exchange(counts_all: np.ndarray, rank: int):
     the OWNER's receive buffer, where this rank's keys of `bin` start (used by the fused path)."""
     counts_all = np.asarray(counts_all, dtype=np.int64)
     world, bins = counts_all.shape
-    owner = choose_owner(counts_all.sum(axis=0), world)
+    owner = choose_owner(counts_all.sum(axis=0), world) if owner is None else np.asarray(owner, dtype=np.int64)
     matrix = np.zeros((world, world), dtype=np.int64)  # matrix[src][dst]
     for dst in range(world):
         matrix[:, dst] = counts_all[:, owner == dst].sum(axis=1)
@@ -96,6 +96,40 @@ def plan_exchange(counts_all: np.ndarray, rank: int):
             "src_base": src_base, "narrow_bits": narrow_bits}
 
 
+SAMPLE_PER_RANK = 8192
+
+
+def sample_indices(n_local: int, m: int = SAMPLE_PER_RANK) -> np.ndarray:
+    """m positions spread over a shard: one per stride, at a position inside the stride that
+    changes from sample to sample (so periodic inputs do not alias with the stride)."""
+    if n_local <= 0:
+        return np.zeros(0, dtype=np.int64)
+    i = np.arange(m, dtype=np.int64)
+    base = (i * n_local) // m
+    stride = max(n_local // m, 1)
+    jitter = ((i * 2654435761) & 0xFFFFFFFF) % stride
+    return np.minimum(base + jitter, n_local - 1)
+
+
+def value_thresholds(sorted_sample: np.ndarray, world: int) -> np.ndarray:
+    """world-1 non-decreasing thresholds t_j in [0, 2^32] from a sorted sample of the keys: a key
+    goes to shard #{j : t_j <= key}.  Cut j aims at the sample's j/world quantile and is moved to
+    the nearer end of the run of equal values around it (t = v: the run goes right, t = v+1: left),
+    so a value is never split and ties stay stable."""
+    s = np.asarray(sorted_sample).astype(np.int64)
+    m = s.size
+    out = np.zeros(max(world - 1, 0), dtype=np.int64)
+    if m == 0:
+        return out
+    for j in range(1, world):
+        q = (j * m) // world
+        v = int(s[min(q, m - 1)])
+        lo = int(np.searchsorted(s, v, side="left"))
+        hi = int(np.searchsorted(s, v, side="right"))
+        out[j - 1] = v if (q - lo) <= (hi - q) else v + 1
+    return np.maximum.accumulate(out)
+
+
 # ---------------------------------------------------------------------------------------------
 class DeviceOps:
     """The product's device operations: libb200sort through the C ABI."""
@@ -116,6 +150,12 @@ class DeviceOps:
         if vals is None:
             return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
         return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws)
+
+    def route(self, keys, thresholds):
+        return self.api.route(keys, thresholds)
+
+    def sample(self, keys, idx):
+        return keys[torch.from_numpy(idx).to(keys.device)]
 
     def empty(self, n):
         return torch.empty(n, dtype=torch.int32, device="cuda")
@@ -147,7 +187,7 @@ class ShardedSorter:
     of `group`."""
 
     def __init__(self, group=None, per_rank_capacity: int = 0, nbits: int = 8, fused: bool = False,
-                 ops=None, time_phases: bool = True, allow_narrow: bool = True):
+                 ops=None, time_phases: bool = True, allow_narrow: bool = True, balance_threshold: float = 1.2):
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -157,6 +197,10 @@ class ShardedSorter:
         self.capacity = int(per_rank_capacity)
         self.fused = bool(fused) and self.on_gpu
         self.allow_narrow = allow_narrow
+        # bin-edge splitters leaving one shard above balance_threshold x the mean switch the sort
+        # to value splitters taken from a sample (0 = never)
+        self.balance_threshold = float(balance_threshold)
+        self.route_dump = None
         self.timer = PhaseTimer(time_phases and self.on_gpu)
         self.last_plan = None
         self.recv = None
@@ -250,14 +294,12 @@ class ShardedSorter:
             self.out_v[:n_local].copy_(vals)
             return self.out[:n_local], self.out_v[:n_local]
         plan = plan_exchange(counts_all, rank)
+        total = int(plan["totals"].sum())
+        plan["imbalance"] = float(plan["totals"].max()) * world / max(total, 1)
+        if world > 1 and self.balance_threshold > 0 and plan["imbalance"] > self.balance_threshold:
+            return self._sort_by_value_splitters(keys, vals, counts_all.sum(axis=1))
         self.last_plan = plan
-        need = int(plan["totals"].max())
-        if self.recv is None or need > self.capacity:
-            if self.fused and self.recv is not None:
-                raise RuntimeError(f"receive capacity {self.capacity} < {need}: construct ShardedSorter with a larger per_rank_capacity")
-            self._allocate(max(need, int(n_local * 1.05) + 1024))
-        if vals is not None:
-            self._allocate_values()
+        self._ensure_capacity(plan, n_local, vals)
         t.mark("splitters")
 
         my_total = plan["my_total"]
@@ -295,9 +337,21 @@ class ShardedSorter:
             if vals is not None:
                 self._all_to_all(self.recv_v[:my_total], part_v, plan["recv_counts"], plan["send_counts"])
             t.mark("exchange")
+        return self._local_sort(my_total, vals is not None)
 
+    def _ensure_capacity(self, plan, n_local, vals):
+        need = int(plan["totals"].max())
+        if self.recv is None or need > self.capacity:
+            if self.fused and self.recv is not None:
+                raise RuntimeError(f"receive capacity {self.capacity} < {need}: construct ShardedSorter with a larger per_rank_capacity")
+            self._allocate(max(need, int(n_local * 1.05) + 1024))
+        if vals is not None:
+            self._allocate_values()
+
+    def _local_sort(self, my_total, pairs):
+        ops, t = self.ops, self.timer
         out = self.out[:my_total]
-        if vals is None:
+        if not pairs:
             if my_total:
                 ops.sort(self.recv[:my_total], self.nbits, out)
             t.mark("local_sort")
@@ -307,6 +361,74 @@ class ShardedSorter:
             ops.sort(self.recv[:my_total], self.nbits, out, vals=self.recv_v[:my_total], out_vals=out_v)
         t.mark("local_sort")
         return out, out_v
+
+    def _sort_by_value_splitters(self, keys, vals, shard_sizes):
+        """Skewed keys: the edges of the 256 bins of the partition byte cannot balance the shards
+        (a heavy bin is never split).  Splitters become key VALUES taken from a sample of every
+        shard; each key's destination (b200sort_route) is then the key of a stable digit pass that
+        carries the real keys -- and, in a second pass, the values -- to their owners.  Costs one
+        extra read+write of the shard; only a single value heavier than 1/G of the input can still
+        unbalance the result (a value is never split, which keeps the sort stable)."""
+        ops, world, rank, t = self.ops, self.world, self.rank, self.timer
+        n_local = keys.numel()
+        m = SAMPLE_PER_RANK
+        idx = sample_indices(n_local, m)
+        mine = ops.sample(keys, idx) if n_local else ops.empty(m).zero_()
+        gathered = ops.empty(world * m)
+        dist.all_gather_into_tensor(gathered, mine.contiguous(), group=self.group)
+        valid = [r for r in range(world) if int(shard_sizes[r]) > 0]
+        pool = torch.cat([gathered[r * m:(r + 1) * m] for r in valid])
+        pool_sorted = ops.sort(pool, 8, ops.empty(pool.numel()))
+        sample = pool_sorted.cpu().numpy().view(np.uint32)
+        thresholds = value_thresholds(sample, world)
+
+        bits = max(1, (world - 1).bit_length())
+        route = ops.route(keys, thresholds)
+        hist = ops.histogram(route, 0, bits)
+        counts = hist.to(torch.int64) & 0xFFFFFFFF
+        allc = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
+        dist.all_gather_into_tensor(allc, counts, group=self.group)
+        counts_all = allc.cpu().numpy().reshape(world, -1)
+        owner = np.minimum(np.arange(1 << bits), world - 1)
+        plan = plan_exchange(counts_all, rank, owner=owner)
+        plan["narrow_bits"] = 0
+        plan["value_thresholds"] = thresholds
+        total = int(plan["totals"].sum())
+        plan["imbalance"] = float(plan["totals"].max()) * world / max(total, 1)
+        self.last_plan = plan
+        self.partition_bits = bits
+        self._ensure_capacity(plan, n_local, vals)
+        if self.part is None or self.part.numel() < n_local:
+            self.part = ops.empty(max(n_local, 1))
+        if self.route_dump is None or self.route_dump.numel() < n_local:
+            self.route_dump = ops.empty(max(n_local, 1))
+        t.mark("splitters")
+
+        my_total = plan["my_total"]
+        if self.fused:
+            # the route array itself stays local (dump), the carried array goes to the peers
+            local_off = np.concatenate([[0], np.cumsum(counts_all[rank])[:-1]]).astype(np.int64)
+            dump_addr = self.route_dump.data_ptr() + 4 * local_off
+            peer = np.array([self.peer_ptrs[int(o)] for o in owner], dtype=np.int64) + 4 * plan["bin_recv_offset"]
+            self.symm.barrier(channel=0)
+            ops.digit_pass(route, 0, bits, bin_dst=torch.from_numpy(np.concatenate([dump_addr, peer])).to("cuda"), vals=keys)
+            if vals is not None:
+                peer_v = np.array([self.peer_ptrs_v[int(o)] for o in owner], dtype=np.int64) + 4 * plan["bin_recv_offset"]
+                ops.digit_pass(route, 0, bits, bin_dst=torch.from_numpy(np.concatenate([dump_addr, peer_v])).to("cuda"), vals=vals)
+            self.symm.barrier(channel=1)
+            t.mark("partition+exchange")
+        else:
+            dump = self.route_dump[:n_local]
+            _, part = ops.digit_pass(route, 0, bits, out=dump, vals=keys, out_vals=self.part[:n_local])
+            t.mark("partition")
+            self._all_to_all(self.recv[:my_total], part, plan["recv_counts"], plan["send_counts"])
+            if vals is not None:
+                if self.part_v is None or self.part_v.numel() < n_local:
+                    self.part_v = ops.empty(max(n_local, 1))
+                _, part_v = ops.digit_pass(route, 0, bits, out=dump, vals=vals, out_vals=self.part_v[:n_local])
+                self._all_to_all(self.recv_v[:my_total], part_v, plan["recv_counts"], plan["send_counts"])
+            t.mark("exchange")
+        return self._local_sort(my_total, vals is not None)
 
     def _all_to_all(self, recv, send, recv_counts, send_counts):
         rc = [int(c) for c in recv_counts]
@@ -351,6 +473,10 @@ class ShardedSorter:
                 rep["egress_gbs_this_rank"] = sent / (rep[key] * 1e-3) / 1e9
             rep["exchange"] = "fused peer stores" if self.fused else "nccl all_to_all_single"
             rep["partition_bits"] = int(plan["narrow_bits"]) if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
+            if "value_thresholds" in plan:
+                rep["partition_bits"] = int(self.partition_bits)
+                rep["splitters"] = "values from a sample"
+            rep["imbalance"] = float(plan.get("imbalance", 0.0))
             rep["shard_sizes"] = [int(x) for x in plan["totals"]]
             rep["partition_shift"] = int(getattr(self, "partition_shift", 32 - TOP_BITS))
         return rep

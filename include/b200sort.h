@@ -142,6 +142,15 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
                         const uint64_t *d_bin_dst, void *d_temp, size_t temp_bytes,
                         void *stream);
 
+/* d_route[i] = number of thresholds <= d_keys[i], for `count` (<= 255) non-decreasing 64-bit
+ * thresholds in [0, 2^32]: the destination shard of every key under VALUE splitters.  Used by
+ * the multi-GPU drivers when the bin-edge splitters of the partition byte leave the shards
+ * unbalanced (skewed keys): the route array is then the key of a digit pass
+ * (b200sort_digit_pass, shift 0) that carries the real keys as values to their owners.
+ * No counterpart in the reference (single GPU). */
+int b200sort_route(const uint32_t *d_keys, uint64_t n, const uint64_t *d_thresholds, int count,
+                   uint32_t *d_route, void *stream);
+
 /* Device-wide exclusive prefix sum of uint32 (mod 2^32), one pass, decoupled look-back.  The
  * public form of the reference's scan stage: scan() + scanBlocks + addScannedBlockSumsToScannedBlocks
  * with its host round trip (SourceCode/Parallel7.cu:408-528), and of Docs/Snippets/

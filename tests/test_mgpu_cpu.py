@@ -99,6 +99,14 @@ class NumpyOps:
         out_vals.numpy().view(np.uint32)[:] = vo
         return out, out_vals
 
+    def route(self, keys, thresholds):
+        k = keys.numpy().view(np.uint32).astype(np.int64)
+        r = np.searchsorted(np.asarray(thresholds, dtype=np.int64), k, side="right")
+        return torch.from_numpy(r.astype(np.int32))
+
+    def sample(self, keys, idx):
+        return keys[torch.from_numpy(idx)]
+
     def empty(self, n):
         return torch.empty(n, dtype=torch.int32)
 
@@ -111,7 +119,13 @@ def _np_verify(t):
 
 
 def _make(O, kind, count, first, total):
-    """small16 / small8: uniform keys with constant (zero) high bytes -- the partition digit must move down."""
+    """small16 / small8: uniform keys with constant (zero) high bytes -- the partition digit must move down.
+    A "vs:" prefix only changes the sorter (value splitters forced), not the data."""
+    kind = kind.split(":")[-1]
+    if kind == "heavybin":      # 90 % of the keys share one top byte but differ below it
+        k = O.generate("uniform", count, first=first, total=total)
+        heavy = (O.generate("uniform", count, first=first + total, total=2 * total) % np.uint32(10)) != 0
+        return np.where(heavy, (k & np.uint32(0x00FFFFFF)) | np.uint32(0x5A000000), k)
     if kind == "small16":
         return O.generate("uniform", count, first=first, total=total) & np.uint32(0xFFFF)
     if kind == "small8":
@@ -128,9 +142,11 @@ def _worker(rank, world, port, kind, n_total, out_dir):
     first = rank * per
     count = per if rank < world - 1 else n_total - first
     keys = torch.from_numpy(_make(O, kind, count, first, n_total).view(np.int32))
-    sorter = mgpu.ShardedSorter(dist.group.WORLD, nbits=8, ops=NumpyOps(), time_phases=False)
+    sorter = mgpu.ShardedSorter(dist.group.WORLD, nbits=8, ops=NumpyOps(), time_phases=False,
+                                balance_threshold=1.0 if kind.startswith("vs:") else 1.2)
     res = sorter.sort(keys)
     key_shift = sorter.partition_shift
+    by_value = "value_thresholds" in sorter.last_plan
     ok = mgpu.verify_sharded(res, keys, verify_fn=_np_verify)
     # a corrupted shard must be caught
     if res.numel() > 2:
@@ -149,7 +165,8 @@ def _worker(rank, world, port, kind, n_total, out_dir):
     pk, pv = sorter.sort_pairs(kk, vv)
     np.save(os.path.join(out_dir, f"pairs_k{rank}.npy"), pk.numpy().view(np.uint32).copy())
     np.save(os.path.join(out_dir, f"pairs_v{rank}.npy"), pv.numpy().view(np.uint32).copy())
-    np.save(os.path.join(out_dir, f"flags{rank}.npy"), np.array([ok, caught, key_shift]))
+    np.save(os.path.join(out_dir, f"flags{rank}.npy"), np.array([ok, caught, key_shift, by_value,
+                                                                 "value_thresholds" in sorter.last_plan]))
     dist.destroy_process_group()
 
 
@@ -160,7 +177,9 @@ def _free_port():
 
 
 @pytest.mark.parametrize("kind,n_total", [("uniform", 200003), ("zipf", 120001), ("all_equal", 5000),
-                                          ("sorted", 70000), ("small16", 90001), ("small8", 30000)])
+                                          ("sorted", 70000), ("small16", 90001), ("small8", 30000),
+                                          ("heavybin", 150001), ("vs:uniform", 100003), ("vs:zipf", 90001),
+                                          ("vs:unique16", 60000), ("vs:sorted", 50001)])
 def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     import oracle as O
     world = 2
@@ -171,13 +190,38 @@ def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     assert np.array_equal(np.concatenate(shards), O.sort_keys(whole, 8))       # concatenation in rank order
     assert all(f[0] for f in flags), "verify_sharded rejected a correct result"
     assert all(f[1] for f in flags), "verify_sharded accepted a corrupted result"
-    if kind in ("uniform", "small16", "small8", "all_equal"):
-        assert abs(len(shards[0]) - len(shards[1])) < 0.02 * n_total + 2          # balanced split
+    if kind in ("uniform", "small16", "small8", "all_equal", "heavybin", "vs:uniform", "vs:sorted"):
+        assert abs(len(shards[0]) - len(shards[1])) < 0.03 * n_total + 2          # balanced split
     expected_shift = {"small16": 8, "small8": 0, "all_equal": 0}.get(kind, 24)
     assert all(int(f[2]) == expected_shift for f in flags)                        # partition digit moved down
+    if kind.startswith("vs:") or kind == "heavybin":
+        assert all(int(f[3]) for f in flags), "value splitters were expected for the keys sort"
     # pairs: concatenation == stable sort of (masked key, global index)
     pk = np.concatenate([np.load(tmp_path / f"pairs_k{r}.npy") for r in range(world)])
     pv = np.concatenate([np.load(tmp_path / f"pairs_v{r}.npy") for r in range(world)])
     mk = whole & np.uint32(0xFF0000FF)
     rk, rv = O.sort_pairs(mk, np.arange(n_total, dtype=np.uint32), 8)
     assert np.array_equal(pk, rk) and np.array_equal(pv, rv)
+
+
+def test_value_thresholds_and_sample_indices():
+    rng = np.random.default_rng(5)
+    s = np.sort(rng.integers(0, 1 << 32, 4096, dtype=np.uint64))
+    for world in (2, 3, 4, 8):
+        t = mgpu.value_thresholds(s, world)
+        assert t.shape == (world - 1,) and np.all(np.diff(t) >= 0)
+        shares = np.bincount(np.searchsorted(t, s.astype(np.int64), side="right"), minlength=world)
+        assert shares.max() - shares.min() <= 2
+    # runs of equal values are never split; the cut goes to the nearer end of the run
+    s = np.sort(np.repeat(np.array([5, 9, 2 ** 32 - 1], dtype=np.uint64), [700, 200, 100]))
+    t = mgpu.value_thresholds(s, 4)
+    assert list(t) == [5, 6, 9] or list(t) == [5, 6, 6] or np.all(np.isin(t, [5, 6, 9, 10, 2 ** 32 - 1, 2 ** 32]))
+    dest = np.searchsorted(t, s.astype(np.int64), side="right")
+    for v in (5, 9, 2 ** 32 - 1):
+        assert len(set(dest[s == v])) == 1
+    assert mgpu.value_thresholds(np.full(64, 2 ** 32 - 1, dtype=np.uint64), 2)[0] in (2 ** 32 - 1, 2 ** 32)
+    assert mgpu.value_thresholds(np.zeros(0, dtype=np.uint64), 4).shape == (3,)
+    for n_local in (1, 7, 8192, 8193, 10 ** 6 + 3):
+        idx = mgpu.sample_indices(n_local, 8192)
+        assert idx.size == 8192 and idx.min() >= 0 and idx.max() < n_local and np.all(np.diff(idx) >= 0)
+    assert mgpu.sample_indices(0).size == 0

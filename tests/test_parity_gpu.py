@@ -394,3 +394,22 @@ def test_device_entry_points_are_reentrant_across_host_threads_and_streams(rs, o
         want = np.sort(j["keys"])
         for o in j["out"]:
             assert np.array_equal(to_host(o), want)
+
+
+def test_route_counts_thresholds_below_or_equal(rs, oracle):
+    import torch
+    rng = np.random.default_rng(22)
+    k = rng.integers(0, 1 << 32, 100003, dtype=np.uint64).astype(np.uint32)
+    k[:5] = [0, 1, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF]
+    for thresholds in ([], [0], [1 << 32], [0x80000000], [5, 5, 1 << 31, (1 << 32) - 1, 1 << 32],
+                       sorted(int(x) for x in rng.integers(0, 1 << 32, 7, dtype=np.uint64)),
+                       sorted(int(x) for x in rng.integers(0, 1 << 32, 200, dtype=np.uint64))):
+        got = to_host(rs.route(to_dev(k), thresholds))
+        want = np.searchsorted(np.asarray(thresholds, dtype=np.int64), k.astype(np.int64), side="right")
+        assert np.array_equal(got, want.astype(np.uint32)), thresholds[:4]
+    # route as the key of a digit pass that carries the real keys: a stable partition by value range
+    t = [1 << 30, 1 << 31, 3 << 30]
+    r = rs.route(to_dev(k), t)
+    _, carried = rs.digit_pass(r, 0, 2, vals=to_dev(k))
+    want = k[np.argsort(k >> 30, kind="stable")]
+    assert np.array_equal(to_host(carried), want)

@@ -26,13 +26,20 @@ def main():
     import oracle as O
     report = {"world": world}
     for fused in (False, True):
-        for kind, log2n in (("uniform", 24), ("zipf", 22), ("unique16", 20), ("all_equal", 18), ("iota", 20)):
+        for kind, log2n in (("uniform", 24), ("zipf", 22), ("unique16", 20), ("all_equal", 18), ("iota", 20),
+                            ("heavybin", 22)):
             total = (1 << log2n) + 12345
             per = total // world
             first = rank * per
             count = per if rank < world - 1 else total - first
             cdf = O.zipf_cdf() if kind == "zipf" else None
-            keys = rs.generate(kind, count, first=first, total=total, zipf_cdf=cdf)
+            if kind == "heavybin":   # 90 % of the keys share one top byte and differ below it
+                keys = rs.generate("uniform", count, first=first, total=total)
+                pick = rs.generate("uniform", count, first=first + total, total=2 * total)
+                heavy = torch.remainder(pick.to(torch.int64) & 0xFFFFFFFF, 10) != 0
+                keys = torch.where(heavy, (keys & 0x00FFFFFF) | 0x5A000000, keys)
+            else:
+                keys = rs.generate(kind, count, first=first, total=total, zipf_cdf=cdf)
             sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=total + 1024, nbits=8, fused=fused)
             res = sorter.sort(keys)
             res2 = sorter.sort(keys)                      # buffers are reused correctly
@@ -58,10 +65,12 @@ def main():
             pad[off:off + res.numel()] = res
             dist.all_reduce(pad)                          # disjoint slices: sum == concatenation
             if rank == 0:
-                whole = O.generate(kind, total, total=total)
+                whole = full.cpu().numpy().view(np.uint32)
                 exact = bool(np.array_equal(pad.cpu().numpy().view(np.uint32), O.sort_keys(whole, 8)))
                 report[f"{'fused' if sorter.fused else 'nccl'}:{kind}:2^{log2n}"] = {
                     "bit_exact": exact, "verify": ok, "shards": [int(x) for x in sizes.tolist()],
+                    "splitters": "values" if "value_thresholds" in sorter.last_plan else "bin edges",
+                    "imbalance": round(float(sorter.last_plan.get("imbalance", 0.0)), 4),
                     "requested_fused": fused, "fused_error": getattr(sorter, "fused_error", None)}
                 assert exact and ok, (kind, fused)
             del sorter
