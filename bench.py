@@ -180,9 +180,11 @@ def workload_config(args, n_gpus: int) -> dict:
                 "n": 1 << args.log2n, "nbits": args.nbits, "distribution": dist,
                 "l2": "inputs larger than L2 (1 GiB of keys vs 126 MB), no flush needed"}
     total_log2 = args.log2n_multi
-    return {"workload": f"2^{total_log2} uniform uint32 keys sharded over {n_gpus} B200: top-digit "
-                        f"histogram + all-reduce splitters, MSD partition, NVLink all-to-all, local LSD sort",
-            "n": 1 << total_log2, "nbits": args.nbits, "distribution": "uniform",
+    what = "key+value pairs" if args.workload == "pairs" else "keys"
+    dist = "uniform" if args.workload == "pairs" else args.workload
+    return {"workload": f"2^{total_log2} {dist} uint32 {what} sharded over {n_gpus} B200: top-digit "
+                        f"histogram + all-gather splitters, MSD partition, NVLink all-to-all, local LSD sort",
+            "n": 1 << total_log2, "nbits": args.nbits, "distribution": dist,
             "l2": "inputs larger than L2"}
 
 
@@ -332,12 +334,24 @@ def run_multi(args):
     rs.load()
     total = 1 << args.log2n_multi
     per = total // world
-    keys = rs.generate("uniform", per, first=rank * per, total=total)
-    sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * 1.02) + (1 << 20),
+    pairs = args.workload == "pairs"
+    kind = "uniform" if pairs else args.workload
+    cdf = None
+    if kind == "zipf":
+        import oracle as O  # the CDF table of the synthetic Zipf workload (input generation only)
+        cdf = O.zipf_cdf()
+    keys = rs.generate(kind, per, first=rank * per, total=total, zipf_cdf=cdf)
+    vals = torch.arange(rank * per, (rank + 1) * per, dtype=torch.int64, device="cuda").to(torch.int32) if pairs else None
+    slack = 1.02 if kind == "uniform" else 1.6      # skewed keys: value splitters never split one value
+    sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * slack) + (1 << 20),
                                 nbits=args.nbits, fused=not args.no_fused, allow_narrow=not args.no_narrow)
+
+    def sort_once():
+        return sorter.sort(keys) if not pairs else sorter.sort_pairs(keys, vals)[0]
+
     result = None
     for _ in range(args.warmup):
-        result = sorter.sort(keys)
+        result = sort_once()
     torch.cuda.synchronize(); dist.barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = rs.launch_count()
@@ -345,7 +359,7 @@ def run_multi(args):
     dist.barrier(); torch.cuda.synchronize()
     start.record()
     for _ in range(args.steps):
-        result = sorter.sort(keys)
+        result = sort_once()
     stop.record()
     torch.cuda.synchronize(); dist.barrier()
     ms = torch.tensor([start.elapsed_time(stop)], device="cuda", dtype=torch.float64)
