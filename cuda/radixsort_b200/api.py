@@ -123,7 +123,7 @@ def sort_pairs_by_devices(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, numBi
 
 
 MGPU_STAT_NAMES = ("upload_ms", "histogram_ms", "plan_ms", "partition_ms", "exchange_wait_ms", "local_sort_ms",
-                   "download_ms", "partition_shift", "partition_bits", "imbalance", "devices")
+                   "download_ms", "partition_shift", "partition_bits", "imbalance", "devices", "value_splitters")
 
 
 def mgpu_last_stats() -> dict:

@@ -488,6 +488,8 @@ int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
 
 }  // namespace
 
+std::atomic<int> g_mgpu_balance_permille{1200};
+
 int set_error(int code, const char *what) { return fail(code, what); }
 int set_cuda_error(cudaError_t e, const char *what) { return fail_cuda(e, what); }
 void set_error_message(const char *message) { g_last_error = message ? message : ""; }
@@ -555,6 +557,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.narrow_variant = value;
         return 0;
     }
+    if (!strcmp(name, "mgpu_balance_permille")) {
+        if (value < 0) return B200SORT_EINVAL;
+        g_mgpu_balance_permille = value;
+        return 0;
+    }
     if (!strcmp(name, "hist_ctas_per_sm")) {
         if (value < 1 || value > 4) return B200SORT_EINVAL;
         g_params.hist_ctas_per_sm = value;
@@ -568,6 +575,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "variant")) return g_params.variant;
     if (!strcmp(name, "portion_tiles")) return g_params.portion_tiles;
     if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
+    if (!strcmp(name, "mgpu_balance_permille")) return g_mgpu_balance_permille.load();
     if (!strcmp(name, "num_variants")) return kNumVariants;
     if (!strcmp(name, "effective_variant")) return check_device() ? std::max(g_params.variant, 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();

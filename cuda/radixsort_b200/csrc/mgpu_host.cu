@@ -75,12 +75,12 @@ enum { EV_START = 0, EV_UPLOADED, EV_HIST, EV_PLANNED, EV_PARTITIONED, EV_EXCHAN
 struct Shard {
     int dev = -1;
     cudaStream_t stream = nullptr;
-    Buf in_k, in_v, recv_k, recv_v, out_k, out_v, temp, small;
+    Buf in_k, in_v, recv_k, recv_v, out_k, out_v, temp, small, route, dump;
     void *stage[kSlots] = {nullptr, nullptr};
     cudaEvent_t stage_ev[kSlots] = {nullptr, nullptr};
     cudaEvent_t ev[EV_COUNT] = {};
     uint32_t *h_counts = nullptr;   // pinned [kPartBins]
-    uint64_t *h_bin_dst = nullptr;  // pinned [2 * kPartBins]
+    uint64_t *h_bin_dst = nullptr;  // pinned [4 * kPartBins]
     // per call
     uint64_t first = 0, count = 0;  // shard of the input
     uint64_t recv = 0, out_first = 0;
@@ -102,6 +102,7 @@ void release_shard(Shard &s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     s.in_k.release(); s.in_v.release(); s.recv_k.release(); s.recv_v.release();
     s.out_k.release(); s.out_v.release(); s.temp.release(); s.small.release();
+    s.route.release(); s.dump.release();
     for (int i = 0; i < kSlots; ++i) {
         if (s.stage[i]) cudaFreeHost(s.stage[i]);
         if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
@@ -130,8 +131,8 @@ int prepare_shard(Shard &s, int dev) {
     for (auto &e : s.ev)
         if (!e) CU(cudaEventCreate(&e));
     if (!s.h_counts) CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_counts), kPartBins * sizeof(uint32_t)));
-    if (!s.h_bin_dst) CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_bin_dst), 2 * kPartBins * sizeof(uint64_t)));
-    RC(s.small.ensure(8192));  // [hist: kPartBins u32 | pad | bin_dst: 2*kPartBins u64]
+    if (!s.h_bin_dst) CU(cudaMallocHost(reinterpret_cast<void **>(&s.h_bin_dst), 4 * kPartBins * sizeof(uint64_t)));
+    RC(s.small.ensure(8192));  // [hist: kPartBins u32 | pad | bin_dst: 2*kPartBins u64 (4*bins by value) | thresholds @6144]
     return 0;
 }
 
@@ -282,14 +283,36 @@ int mark(Shard &s, int which) {
     return 0;
 }
 
+// Value splitters for skewed keys (the host-side twin of mgpu.py:value_thresholds): G-1
+// non-decreasing thresholds in [0, 2^32] from a sorted sample; a key goes to shard
+// #{j : t_j <= key}.  Cut j aims at the j/G quantile of the sample and moves to the nearer end of
+// the run of equal values around it, so a value is never split (ties stay in input order).
+std::vector<uint64_t> value_thresholds(const std::vector<uint32_t> &sample, int G) {
+    std::vector<uint64_t> t(G > 1 ? G - 1 : 0, 0);
+    const size_t m = sample.size();
+    if (m == 0) return t;
+    for (int j = 1; j < G; ++j) {
+        const size_t q = (size_t)j * m / G;
+        const uint32_t v = sample[std::min(q, m - 1)];
+        const size_t lo = std::lower_bound(sample.begin(), sample.end(), v) - sample.begin();
+        const size_t hi = std::upper_bound(sample.begin(), sample.end(), v) - sample.begin();
+        t[j - 1] = (q - lo) <= (hi - q) ? (uint64_t)v : (uint64_t)v + 1;
+        if (j > 1) t[j - 1] = std::max(t[j - 1], t[j - 2]);
+    }
+    return t;
+}
+
+constexpr size_t kSamplePerShard = 8192;
+
 // Histogram of the partition digit on every shard, splitters, then one digit pass per shard that
 // writes each bin into its owner's receive buffer.  On return every stream has waited for all
 // partitions and the shards know their received range.
-int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool pairs, int &part_shift_out,
-                           int &part_bits_out, uint64_t &max_recv_out, double &plan_ms_out) {
+int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64_t n, int nbits, bool pairs,
+                           int &part_shift_out, int &part_bits_out, uint64_t &max_recv_out, double &plan_ms_out,
+                           bool &by_value_out) {
     const int G = (int)sh.size();
     // ---- partition digit: the highest byte in which the keys differ -----------------------------
-    std::vector<uint64_t> counts((size_t)G * kPartBins);
+    std::vector<uint64_t> counts((size_t)G * kPartBins);  // [src][bin], re-shaped below when the digit narrows
     std::vector<uint64_t> global(kPartBins);
     int shift = 32 - kPartBits;
     for (;;) {
@@ -315,12 +338,87 @@ int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool p
 
     // ---- plan ----------------------------------------------------------------------------------
     const auto plan_t0 = std::chrono::steady_clock::now();
+    int bins = kPartBins, part_bits = kPartBits, part_shift = shift;
     std::vector<int> owner(kPartBins);
     choose_owner(global.data(), kPartBins, G, owner.data());
     std::vector<uint64_t> matrix((size_t)G * G, 0);  // [src][dst]
-    for (int i = 0; i < G; ++i)
-        for (int b = 0; b < kPartBins; ++b) matrix[(size_t)i * G + owner[b]] += counts[(size_t)i * kPartBins + b];
-    uint64_t max_recv = 0, running_out = 0;
+    auto fill_matrix = [&]() {
+        std::fill(matrix.begin(), matrix.end(), 0);
+        for (int i = 0; i < G; ++i)
+            for (int b = 0; b < bins; ++b) matrix[(size_t)i * G + owner[b]] += counts[(size_t)i * bins + b];
+        uint64_t mx = 0;
+        for (int d = 0; d < G; ++d) {
+            uint64_t tot = 0;
+            for (int i = 0; i < G; ++i) tot += matrix[(size_t)i * G + d];
+            mx = std::max(mx, tot);
+        }
+        return mx;
+    };
+    uint64_t max_recv = fill_matrix();
+
+    const int permille = g_mgpu_balance_permille.load();
+    const bool by_value = permille > 0 && (double)max_recv * G > (double)n * permille / 1000.0;
+    if (by_value) {
+        // Skewed keys: bin edges of one byte cannot balance the shards.  Splitters become key values
+        // from a sample of the host array; b200sort_route turns every key into its destination, and
+        // that route array is the KEY of the partition pass below, which carries the real keys.
+        std::vector<uint32_t> sample;
+        sample.reserve((size_t)G * kSamplePerShard);
+        for (auto &s : sh) {
+            if (!s.count) continue;
+            const uint64_t stride = std::max<uint64_t>(s.count / kSamplePerShard, 1);
+            for (uint64_t i = 0; i < kSamplePerShard; ++i) {
+                const uint64_t base = (uint64_t)(((unsigned __int128)i * s.count) / kSamplePerShard);
+                const uint64_t at = std::min<uint64_t>(base + ((i * 2654435761ull) & 0xFFFFFFFFull) % stride, s.count - 1);
+                sample.push_back(hk_in[s.first + at]);
+            }
+        }
+        std::sort(sample.begin(), sample.end());  // <= 64 x 8192 sample keys: planning, not the sort
+        const std::vector<uint64_t> thresholds = value_thresholds(sample, G);
+        part_bits = 1;
+        while ((1 << part_bits) < G) ++part_bits;
+        part_shift = 0;
+        bins = 1 << part_bits;
+        for (auto &s : sh) {
+            CU(cudaSetDevice(s.dev));
+            const size_t bytes = align_up(std::max<uint64_t>(s.count, 1) * 4, 256);
+            RC(s.route.ensure(bytes));
+            RC(s.dump.ensure(bytes));
+            uint64_t *d_thr = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 6144);
+            std::copy(thresholds.begin(), thresholds.end(), s.h_bin_dst);  // pinned scratch, re-filled below
+            CU(cudaMemcpyAsync(d_thr, s.h_bin_dst, thresholds.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+            RC(b200sort_route(static_cast<const uint32_t *>(s.in_k.p), s.count, d_thr, (int)thresholds.size(),
+                              static_cast<uint32_t *>(s.route.p), s.stream));
+            uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);
+            RC(b200sort_histogram(static_cast<const uint32_t *>(s.route.p), s.count, 0, part_bits, d_hist, s.temp.p,
+                                  s.temp.bytes, s.stream));
+            CU(cudaMemcpyAsync(s.h_counts, d_hist, bins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        }
+        RC(sync_all(sh));
+        counts.assign((size_t)G * bins, 0);
+        for (int i = 0; i < G; ++i)
+            for (int b = 0; b < bins; ++b) counts[(size_t)i * bins + b] = sh[i].h_counts[b];
+        owner.assign(bins, 0);
+        for (int b = 0; b < bins; ++b) owner[b] = std::min(b, G - 1);
+        max_recv = fill_matrix();
+    } else {
+        // Splitters on the top log2(G) bits (uniform keys, G a power of two): partition with a
+        // log2(G)-bit digit -- G bins instead of 256, long runs per (tile, destination).
+        int lg = 0;
+        while ((1 << (lg + 1)) <= G) ++lg;
+        bool narrow = G > 1 && (1 << lg) == G && lg <= kPartBits;
+        for (int b = 0; narrow && b < kPartBins; ++b) narrow = owner[b] == (b >> (kPartBits - lg));
+        if (narrow) {
+            part_bits = lg;
+            part_shift = shift + kPartBits - lg;
+            bins = G;
+            counts = matrix;  // [src][dst] is the count table of the narrow digit
+            owner.resize(G);
+            for (int b = 0; b < G; ++b) owner[b] = b;
+        }
+    }
+
+    uint64_t running_out = 0;
     for (int d = 0; d < G; ++d) {
         uint64_t tot = 0;
         for (int i = 0; i < G; ++i) tot += matrix[(size_t)i * G + d];
@@ -328,18 +426,7 @@ int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool p
         sh[d].recv = tot;
         sh[d].out_first = running_out;
         running_out += tot;
-        max_recv = std::max(max_recv, tot);
     }
-    // Splitters on the top log2(G) bits (uniform keys, G a power of two): partition with a
-    // log2(G)-bit digit -- G bins instead of 256, long runs per (tile, destination).
-    int lg = 0;
-    while ((1 << (lg + 1)) <= G) ++lg;
-    bool narrow = G > 1 && (1 << lg) == G && lg <= kPartBits;
-    for (int b = 0; narrow && b < kPartBins; ++b) narrow = owner[b] == (b >> (kPartBits - lg));
-    const int part_bits = narrow ? lg : kPartBits;
-    const int part_shift = narrow ? shift + kPartBits - lg : shift;
-    const int part_bins = 1 << part_bits;
-
     for (int d = 0; d < G; ++d) {
         Shard &s = sh[d];
         CU(cudaSetDevice(s.dev));
@@ -357,7 +444,8 @@ int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool p
             s.sorted_k = static_cast<uint32_t *>(s.out_k.p);
             s.sorted_v = static_cast<uint32_t *>(s.out_v.p);
         }
-        const size_t t = std::max(b200sort_temp_bytes(s.recv, nbits, pairs), s.temp.bytes);
+        size_t t = b200sort_temp_bytes(s.recv, nbits, pairs);
+        if (by_value) t = std::max(t, b200sort_temp_bytes(s.count, part_bits, true));
         if (t > s.temp.bytes) RC(s.temp.ensure(align_up(t, 256)));
     }
 
@@ -368,22 +456,42 @@ int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool p
     for (int i = 0; i < G; ++i) {
         Shard &s = sh[i];
         std::vector<uint64_t> at(src_base);
-        for (int b = 0; b < part_bins; ++b) {
-            const int o = narrow ? b : owner[b];
-            const uint64_t cnt = narrow ? matrix[(size_t)i * G + b] : counts[(size_t)i * kPartBins + b];
-            s.h_bin_dst[b] = reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_k.p) + at[o]);
-            s.h_bin_dst[part_bins + b] = pairs ? reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_v.p) + at[o]) : 0;
+        uint64_t local = 0;
+        for (int b = 0; b < bins; ++b) {
+            const int o = owner[b];
+            const uint64_t cnt = counts[(size_t)i * bins + b];
+            const uint64_t to_k = reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_k.p) + at[o]);
+            const uint64_t to_v = pairs ? reinterpret_cast<uint64_t>(static_cast<uint32_t *>(sh[o].recv_v.p) + at[o]) : 0;
+            if (by_value) {  // keys = route (stays here, in the dump buffer), carried = real keys; values in a second pass
+                s.h_bin_dst[b] = reinterpret_cast<uint64_t>(static_cast<uint32_t *>(s.dump.p) + local);
+                s.h_bin_dst[bins + b] = to_k;
+                s.h_bin_dst[2 * bins + b] = s.h_bin_dst[b];
+                s.h_bin_dst[3 * bins + b] = to_v;
+            } else {
+                s.h_bin_dst[b] = to_k;
+                s.h_bin_dst[bins + b] = to_v;
+            }
             at[o] += cnt;
+            local += cnt;
         }
         for (int d = 0; d < G; ++d) src_base[d] += matrix[(size_t)i * G + d];
         CU(cudaSetDevice(s.dev));
         uint64_t *d_bin_dst = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 2048);
-        CU(cudaMemcpyAsync(d_bin_dst, s.h_bin_dst, (size_t)2 * part_bins * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(d_bin_dst, s.h_bin_dst, (size_t)(by_value ? 4 : 2) * bins * sizeof(uint64_t),
+                           cudaMemcpyHostToDevice, s.stream));
         CU(cudaEventRecord(s.ev[EV_PLANNED], s.stream));
-        if (s.count)
+        if (s.count && !by_value)
             RC(b200sort_digit_pass(static_cast<const uint32_t *>(s.in_k.p),
                                    pairs ? static_cast<const uint32_t *>(s.in_v.p) : nullptr, s.count, nullptr, nullptr,
                                    part_shift, part_bits, d_bin_dst, s.temp.p, s.temp.bytes, s.stream));
+        if (s.count && by_value) {
+            RC(b200sort_digit_pass(static_cast<const uint32_t *>(s.route.p), static_cast<const uint32_t *>(s.in_k.p),
+                                   s.count, nullptr, nullptr, 0, part_bits, d_bin_dst, s.temp.p, s.temp.bytes, s.stream));
+            if (pairs)
+                RC(b200sort_digit_pass(static_cast<const uint32_t *>(s.route.p), static_cast<const uint32_t *>(s.in_v.p),
+                                       s.count, nullptr, nullptr, 0, part_bits, d_bin_dst + 2 * bins, s.temp.p,
+                                       s.temp.bytes, s.stream));
+        }
         CU(cudaEventRecord(s.ev[EV_PARTITIONED], s.stream));
     }
     for (int i = 0; i < G; ++i) {
@@ -397,6 +505,7 @@ int partition_and_exchange(std::vector<Shard> &sh, uint64_t n, int nbits, bool p
     part_shift_out = part_shift;
     part_bits_out = part_bits;
     max_recv_out = max_recv;
+    by_value_out = by_value;
     return 0;
 }
 
@@ -494,7 +603,8 @@ int sort_mgpu(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
     int part_shift = 0, part_bits = 0;
     uint64_t max_recv = 0;
     double plan_ms = 0.0;
-    if (G > 1) RC(partition_and_exchange(sh, n, nbits, pairs, part_shift, part_bits, max_recv, plan_ms));
+    bool by_value = false;
+    if (G > 1) RC(partition_and_exchange(sh, hk_in, n, nbits, pairs, part_shift, part_bits, max_recv, plan_ms, by_value));
     else RC(single_shard(sh[0], nbits, pairs, max_recv));
 
     // ---- local sorts, download -------------------------------------------------------------------
@@ -533,6 +643,7 @@ int sort_mgpu(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
     st[8] = part_bits;
     st[9] = (double)max_recv * G / (double)n;
     st[10] = G;
+    st[11] = by_value ? 1.0 : 0.0;
     g.stats_valid = 1;
     return B200SORT_OK;
 }

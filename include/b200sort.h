@@ -94,9 +94,11 @@ int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_i
  * histogram, plan (host clock: splitters, receive buffers), partition kernel, wait for the
  * peers' partitions, local sort, download -- device-event times, each the maximum over the
  * devices, so they need not add up to the call's wall time; out[7] = partition shift,
- * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices.
+ * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices, out[11] = 1 when
+ * the splitters were key values from a sample (skewed keys; see b200sort_route) instead of bin
+ * edges of the partition byte.
  * Returns the number of values written (<= capacity). */
-enum { B200SORT_MGPU_STATS = 11 };
+enum { B200SORT_MGPU_STATS = 12 };
 int b200sort_mgpu_last_stats(double *out, int capacity);
 int b200sort_mgpu_shutdown(void);
 

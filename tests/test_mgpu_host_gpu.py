@@ -115,3 +115,51 @@ def test_bad_devices_are_refused(rs):
     with pytest.raises(rs.RadixSortError):
         rs.sort_by_devices(k, 8, k.copy(), 8, 512, [0, 4096])
     rs.sort_by_devices(k, 8, k.copy(), 8, 512, None)   # every visible device
+
+
+def heavy_bin_keys(oracle, n):
+    """90 % of the keys share one top byte and differ below it: no edge of the 256 top-byte bins
+    can balance the shards."""
+    k = oracle.generate("uniform", n)
+    heavy = (oracle.generate("uniform", n, first=n, total=2 * n) % np.uint32(10)) != 0
+    return np.where(heavy, (k & np.uint32(0x00FFFFFF)) | np.uint32(0x5A000000), k).astype(np.uint32)
+
+
+def test_skewed_keys_switch_to_value_splitters(rs, oracle):
+    n = (1 << 21) + 11
+    k = heavy_bin_keys(oracle, n)
+    want = np.sort(k)
+    for devs in device_sets()[1:]:
+        assert np.array_equal(run(rs, k, 8, devs), want), devs
+        st = rs.mgpu_last_stats()
+        assert st["value_splitters"] == 1 and st["imbalance"] < 1.1, (devs, st)
+    # the same input with the switch disabled: still correct, but one shard takes most of the keys
+    rs.set_param("mgpu_balance_permille", 0)
+    try:
+        assert np.array_equal(run(rs, k, 8, [0, 0, 0, 0]), want)
+        st = rs.mgpu_last_stats()
+        assert st["value_splitters"] == 0 and st["imbalance"] > 2.0
+    finally:
+        rs.set_param("mgpu_balance_permille", 1200)
+    # forced on for balanced and duplicate-heavy inputs alike
+    rs.set_param("mgpu_balance_permille", 1)
+    try:
+        for kind in ("uniform", "zipf", "unique16", "all_equal", "sorted", "reversed"):
+            kk = oracle.generate(kind, (1 << 19) + 3)
+            for devs in ([0, 0], [0, 0, 0], [0, 0, 0, 0, 0]):
+                assert np.array_equal(run(rs, kk, 8, devs), np.sort(kk)), (kind, devs)
+                assert rs.mgpu_last_stats()["value_splitters"] == 1
+    finally:
+        rs.set_param("mgpu_balance_permille", 1200)
+
+
+def test_value_splitters_keep_pairs_stable(rs, oracle):
+    n = (1 << 20) + 5
+    k = heavy_bin_keys(oracle, n) & np.uint32(0xFFFF00FF)      # plenty of duplicates inside the heavy bin
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v, 8)
+    for devs in device_sets()[1:]:
+        ok, ov = np.zeros_like(k), np.zeros_like(v)
+        rs.sort_pairs_by_devices(k, v, n, ok, ov, 8, 512, devs)
+        assert rs.mgpu_last_stats()["value_splitters"] == 1
+        assert np.array_equal(ok, wk) and np.array_equal(ov, wv), devs
