@@ -475,7 +475,8 @@ class ShardedSorter:
             rep["partition_bits"] = int(plan["narrow_bits"]) if self.allow_narrow and plan["narrow_bits"] else TOP_BITS
             if "value_thresholds" in plan:
                 rep["partition_bits"] = int(self.partition_bits)
-                rep["splitters"] = "values from a sample"
+                rep["splitter_kind"] = "values from a sample"
+            rep.setdefault("splitter_kind", "bin edges of the partition byte")
             rep["imbalance"] = float(plan.get("imbalance", 0.0))
             rep["shard_sizes"] = [int(x) for x in plan["totals"]]
             rep["partition_shift"] = int(getattr(self, "partition_shift", 32 - TOP_BITS))
