@@ -293,19 +293,21 @@ def digit_pass(keys, shift: int, bits: int, vals=None, out_keys=None, out_vals=N
     return (out_keys, out_vals) if vals is not None else out_keys
 
 
-def route(keys, thresholds, out=None, stream=None):
-    """out[i] = number of thresholds <= keys[i] (unsigned): b200sort_route.
+def route(keys, values, ties=None, out=None, stream=None):
+    """out[i] = #{j : (values[j], ties[j]) <= (keys[i], i)} (unsigned keys, lexicographic): b200sort_route.
 
-    ``thresholds``: non-decreasing integers in [0, 2^32] (a sequence or a CUDA int64 tensor)."""
+    ``values``: non-decreasing integers in [0, 2^32]; ``ties``: for each cut the local index from
+    which a key EQUAL to the value counts as at-or-above the cut (default 0: the whole run)."""
     torch = _torch()
-    if not torch.is_tensor(thresholds):
-        thresholds = torch.tensor([int(t) for t in thresholds], dtype=torch.int64, device=keys.device)
-    if thresholds.dtype != torch.int64 or not thresholds.is_cuda:
-        raise TypeError("thresholds must be a CUDA int64 tensor")
+    values = [int(v) for v in values]
+    ties = [0] * len(values) if ties is None else [int(t) for t in ties]
+    if len(ties) != len(values):
+        raise ValueError("values and ties differ in length")
+    table = torch.tensor(values + ties, dtype=torch.int64, device=keys.device)
     out = torch.empty_like(keys) if out is None else out
     _lib.check(_lib.load().b200sort_route(_dev_ptr(keys, "keys"), keys.numel(),
-                                          thresholds.data_ptr() if thresholds.numel() else None,
-                                          thresholds.numel(), _dev_ptr(out, "out"), _stream_ptr(stream)))
+                                          table.data_ptr() if table.numel() else None,
+                                          len(values), _dev_ptr(out, "out"), _stream_ptr(stream)))
     return out
 
 

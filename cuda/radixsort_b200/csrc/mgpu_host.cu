@@ -283,21 +283,56 @@ int mark(Shard &s, int which) {
     return 0;
 }
 
-// Value splitters for skewed keys (the host-side twin of mgpu.py:value_thresholds): G-1
-// non-decreasing thresholds in [0, 2^32] from a sorted sample; a key goes to shard
-// #{j : t_j <= key}.  Cut j aims at the j/G quantile of the sample and moves to the nearer end of
-// the run of equal values around it, so a value is never split (ties stay in input order).
-std::vector<uint64_t> value_thresholds(const std::vector<uint32_t> &sample, int G) {
-    std::vector<uint64_t> t(G > 1 ? G - 1 : 0, 0);
-    const size_t m = sample.size();
-    if (m == 0) return t;
+// Value splitters for skewed keys (the host-side twin of mgpu.py:value_splitters): cut j aims at
+// the j/G quantile of the pooled sample and sits at a key value v_j.  Keys equal to v_j go left of
+// the cut when they come from a shard < split[j], right from a shard > split[j], and inside shard
+// split[j] those at local index < pos[j] go left.  Cutting a run of equal keys at a position of the
+// global input order keeps ties in that order and lets one heavy value spread over shards.
+constexpr uint64_t kTieAllLeft = 1ull << 62;
+struct ValueCuts {
+    std::vector<uint64_t> value, pos;
+    std::vector<int> split;
+};
+struct ShardSample {
+    std::vector<uint32_t> key;
+    std::vector<uint64_t> at;  // local index each sample was taken from (ascending)
+};
+ValueCuts value_splitters(const std::vector<uint32_t> &pool_sorted, const std::vector<ShardSample> &by_shard, int G) {
+    ValueCuts c;
+    c.value.assign(G > 1 ? G - 1 : 0, 0);
+    c.pos.assign(c.value.size(), 0);
+    c.split.assign(c.value.size(), 0);
+    const size_t m = pool_sorted.size();
+    if (m == 0) return c;
     for (int j = 1; j < G; ++j) {
-        const size_t q = (size_t)j * m / G;
-        const uint32_t v = sample[std::min(q, m - 1)];
-        const size_t lo = std::lower_bound(sample.begin(), sample.end(), v) - sample.begin();
-        const size_t hi = std::upper_bound(sample.begin(), sample.end(), v) - sample.begin();
-        t[j - 1] = (q - lo) <= (hi - q) ? (uint64_t)v : (uint64_t)v + 1;
-        if (j > 1) t[j - 1] = std::max(t[j - 1], t[j - 2]);
+        const size_t q = std::min((size_t)j * m / G, m - 1);
+        const uint32_t v = pool_sorted[q];
+        const size_t lo = std::lower_bound(pool_sorted.begin(), pool_sorted.end(), v) - pool_sorted.begin();
+        size_t left = q - lo;  // sampled copies of v that belong left of the cut
+        c.value[j - 1] = v;
+        c.split[j - 1] = G;    // default: the whole run goes left
+        for (int r = 0; r < G && c.split[j - 1] == G; ++r) {
+            const ShardSample &sm = by_shard[r];
+            for (size_t i = 0; i < sm.key.size(); ++i) {
+                if (sm.key[i] != v) continue;
+                if (left == 0) {
+                    c.split[j - 1] = r;
+                    c.pos[j - 1] = sm.at[i];
+                    break;
+                }
+                --left;
+            }
+        }
+    }
+    return c;
+}
+// Cuts of one source shard for b200sort_route: `count` values followed by `count` tie indices.
+std::vector<uint64_t> thresholds_for_shard(const ValueCuts &c, int shard) {
+    const size_t count = c.value.size();
+    std::vector<uint64_t> t(2 * count);
+    for (size_t j = 0; j < count; ++j) {
+        t[j] = c.value[j];
+        t[count + j] = shard < c.split[j] ? kTieAllLeft : (shard > c.split[j] ? 0 : c.pos[j]);
     }
     return t;
 }
@@ -362,24 +397,30 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
         // Skewed keys: bin edges of one byte cannot balance the shards.  Splitters become key values
         // from a sample of the host array; b200sort_route turns every key into its destination, and
         // that route array is the KEY of the partition pass below, which carries the real keys.
-        std::vector<uint32_t> sample;
-        sample.reserve((size_t)G * kSamplePerShard);
-        for (auto &s : sh) {
+        std::vector<ShardSample> by_shard(G);
+        std::vector<uint32_t> pool;
+        pool.reserve((size_t)G * kSamplePerShard);
+        for (int g2 = 0; g2 < G; ++g2) {
+            const Shard &s = sh[g2];
             if (!s.count) continue;
             const uint64_t stride = std::max<uint64_t>(s.count / kSamplePerShard, 1);
             for (uint64_t i = 0; i < kSamplePerShard; ++i) {
                 const uint64_t base = (uint64_t)(((unsigned __int128)i * s.count) / kSamplePerShard);
                 const uint64_t at = std::min<uint64_t>(base + ((i * 2654435761ull) & 0xFFFFFFFFull) % stride, s.count - 1);
-                sample.push_back(hk_in[s.first + at]);
+                by_shard[g2].key.push_back(hk_in[s.first + at]);
+                by_shard[g2].at.push_back(at);
             }
+            pool.insert(pool.end(), by_shard[g2].key.begin(), by_shard[g2].key.end());
         }
-        std::sort(sample.begin(), sample.end());  // <= 64 x 8192 sample keys: planning, not the sort
-        const std::vector<uint64_t> thresholds = value_thresholds(sample, G);
+        std::sort(pool.begin(), pool.end());  // <= 64 x 8192 sample keys: planning, not the sort
+        const ValueCuts cuts = value_splitters(pool, by_shard, G);
         part_bits = 1;
         while ((1 << part_bits) < G) ++part_bits;
         part_shift = 0;
         bins = 1 << part_bits;
-        for (auto &s : sh) {
+        for (int g2 = 0; g2 < G; ++g2) {
+            Shard &s = sh[g2];
+            const std::vector<uint64_t> thresholds = thresholds_for_shard(cuts, g2);
             CU(cudaSetDevice(s.dev));
             const size_t bytes = align_up(std::max<uint64_t>(s.count, 1) * 4, 256);
             RC(s.route.ensure(bytes));
@@ -387,7 +428,7 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
             uint64_t *d_thr = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 6144);
             std::copy(thresholds.begin(), thresholds.end(), s.h_bin_dst);  // pinned scratch, re-filled below
             CU(cudaMemcpyAsync(d_thr, s.h_bin_dst, thresholds.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-            RC(b200sort_route(static_cast<const uint32_t *>(s.in_k.p), s.count, d_thr, (int)thresholds.size(),
+            RC(b200sort_route(static_cast<const uint32_t *>(s.in_k.p), s.count, d_thr, (int)(thresholds.size() / 2),
                               static_cast<uint32_t *>(s.route.p), s.stream));
             uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);
             RC(b200sort_histogram(static_cast<const uint32_t *>(s.route.p), s.count, 0, part_bits, d_hist, s.temp.p,

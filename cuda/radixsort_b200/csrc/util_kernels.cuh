@@ -77,26 +77,33 @@ __global__ void __launch_bounds__(256) verify_kernel(const uint32_t *__restrict_
     }
 }
 
-// route[i] = #{j < count : thresholds[j] <= key[i]} for non-decreasing 64-bit thresholds in
-// [0, 2^32]: the destination shard of a key under value splitters (multi-GPU, skewed keys).
+// route[i] = #{j < count : (value[j], tie[j]) <= (key[i], i)} in lexicographic order, for `count`
+// cuts given as thresholds[0 .. count) = values in [0, 2^32] and thresholds[count .. 2*count) =
+// tie indices: a key EQUAL to value[j] counts as >= cut j from local index tie[j] on.  This is the
+// destination shard of a key under value splitters (multi-GPU, skewed keys); the tie index lets a
+// run of equal keys be cut at a position, in input order.  Cuts must be non-decreasing.
 // The result is then used as the KEY of a digit pass that carries the real keys as values.
 constexpr int kMaxRouteThresholds = 255;
 __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                     const uint64_t *__restrict__ thresholds, int count,
                                                     uint32_t *__restrict__ route) {
-    __shared__ uint64_t s_t[kMaxRouteThresholds + 1];
-    for (int j = threadIdx.x; j < count; j += blockDim.x) s_t[j] = thresholds[j];
+    __shared__ uint64_t s_v[kMaxRouteThresholds + 1];
+    __shared__ uint64_t s_c[kMaxRouteThresholds + 1];
+    for (int j = threadIdx.x; j < count; j += blockDim.x) {
+        s_v[j] = thresholds[j];
+        s_c[j] = thresholds[count + j];
+    }
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
         uint32_t r = 0;
         if (count <= 8) {
-            for (int j = 0; j < count; ++j) r += (s_t[j] <= k) ? 1u : 0u;
+            for (int j = 0; j < count; ++j) r += (s_v[j] < k || (s_v[j] == k && s_c[j] <= i)) ? 1u : 0u;
         } else {  // upper bound by bisection
             int lo = 0, hi = count;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (s_t[mid] <= k) lo = mid + 1; else hi = mid;
+                if (s_v[mid] < k || (s_v[mid] == k && s_c[mid] <= i)) lo = mid + 1; else hi = mid;
             }
             r = (uint32_t)lo;
         }

@@ -111,23 +111,52 @@ def sample_indices(n_local: int, m: int = SAMPLE_PER_RANK) -> np.ndarray:
     return np.minimum(base + jitter, n_local - 1)
 
 
-def value_thresholds(sorted_sample: np.ndarray, world: int) -> np.ndarray:
-    """world-1 non-decreasing thresholds t_j in [0, 2^32] from a sorted sample of the keys: a key
-    goes to shard #{j : t_j <= key}.  Cut j aims at the sample's j/world quantile and is moved to
-    the nearer end of the run of equal values around it (t = v: the run goes right, t = v+1: left),
-    so a value is never split and ties stay stable."""
-    s = np.asarray(sorted_sample).astype(np.int64)
+TIE_ALL_LEFT = 1 << 62   # tie index beyond any shard: every key equal to the cut value stays left of the cut
+
+
+def value_splitters(sorted_pool: np.ndarray, samples_by_rank, positions_by_rank, world: int):
+    """Cuts of the key space taken from a sample: returns (values, split_rank, split_pos), each of
+    world-1 entries.
+
+    Cut j aims at the j/world quantile of the pooled sample and sits at a key VALUE v_j.  Keys
+    below v_j go left of the cut, keys above go right.  Keys EQUAL to v_j go left when they come
+    from a source rank < split_rank[j], right from a rank > split_rank[j], and inside rank
+    split_rank[j] those at local index < split_pos[j] go left.  Cutting a run of equal keys at a
+    position of the global input order keeps ties in that order (lower ranks hold lower global
+    indices), so the sort stays stable while one heavy value -- or an all-equal input -- spreads
+    over as many shards as its size asks for.  positions_by_rank[r][i] is the local index the
+    i-th sample of rank r was taken from (ascending)."""
+    s = np.asarray(sorted_pool).astype(np.int64)
     m = s.size
-    out = np.zeros(max(world - 1, 0), dtype=np.int64)
+    values = np.zeros(max(world - 1, 0), dtype=np.int64)
+    split_rank = np.zeros(max(world - 1, 0), dtype=np.int64)
+    split_pos = np.zeros(max(world - 1, 0), dtype=np.int64)
     if m == 0:
-        return out
+        return values, split_rank, split_pos
+    per_rank = [np.asarray(x).astype(np.int64) for x in samples_by_rank]
     for j in range(1, world):
-        q = (j * m) // world
-        v = int(s[min(q, m - 1)])
-        lo = int(np.searchsorted(s, v, side="left"))
-        hi = int(np.searchsorted(s, v, side="right"))
-        out[j - 1] = v if (q - lo) <= (hi - q) else v + 1
-    return np.maximum.accumulate(out)
+        q = min((j * m) // world, m - 1)
+        v = int(s[q])
+        lo = int(np.searchsorted(s, v, side="left"))           # lo <= q < hi: the cut lies inside the run of v
+        left = q - lo                                           # sampled copies of v that belong left of the cut
+        values[j - 1] = v
+        split_rank[j - 1] = world                                # default: the whole run goes left
+        for r in range(world):
+            hits = np.flatnonzero(per_rank[r] == v)
+            if left < hits.size:
+                split_rank[j - 1] = r
+                split_pos[j - 1] = int(positions_by_rank[r][hits[left]])
+                break
+            left -= hits.size
+    return values, split_rank, split_pos
+
+
+def thresholds_for_rank(values, split_rank, split_pos, rank: int):
+    """(values, ties) of one source rank for b200sort_route: a key equal to values[j] is at or above
+    cut j from local index ties[j] on."""
+    split_rank = np.asarray(split_rank, dtype=np.int64)
+    ties = np.where(rank < split_rank, TIE_ALL_LEFT, np.where(rank > split_rank, 0, np.asarray(split_pos, dtype=np.int64)))
+    return np.asarray(values, dtype=np.int64), ties.astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -151,8 +180,8 @@ class DeviceOps:
             return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
         return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws)
 
-    def route(self, keys, thresholds):
-        return self.api.route(keys, thresholds)
+    def route(self, keys, values, ties):
+        return self.api.route(keys, values, ties)
 
     def sample(self, keys, idx):
         return keys[torch.from_numpy(idx).to(keys.device)]
@@ -367,8 +396,8 @@ class ShardedSorter:
         (a heavy bin is never split).  Splitters become key VALUES taken from a sample of every
         shard; each key's destination (b200sort_route) is then the key of a stable digit pass that
         carries the real keys -- and, in a second pass, the values -- to their owners.  Costs one
-        extra read+write of the shard; only a single value heavier than 1/G of the input can still
-        unbalance the result (a value is never split, which keeps the sort stable)."""
+        extra read+write of the shard.  A run of equal keys that straddles a cut is split at a
+        position of the global input order (value_splitters), which keeps ties in that order."""
         ops, world, rank, t = self.ops, self.world, self.rank, self.timer
         n_local = keys.numel()
         m = SAMPLE_PER_RANK
@@ -379,11 +408,15 @@ class ShardedSorter:
         valid = [r for r in range(world) if int(shard_sizes[r]) > 0]
         pool = torch.cat([gathered[r * m:(r + 1) * m] for r in valid])
         pool_sorted = ops.sort(pool, 8, ops.empty(pool.numel()))
-        sample = pool_sorted.cpu().numpy().view(np.uint32)
-        thresholds = value_thresholds(sample, world)
+        by_rank = gathered.cpu().numpy().view(np.uint32).reshape(world, m)
+        empty = np.zeros(0, dtype=np.uint32)
+        values, split_rank, split_pos = value_splitters(
+            pool_sorted.cpu().numpy().view(np.uint32), [by_rank[r] if r in valid else empty for r in range(world)],
+            [sample_indices(int(shard_sizes[r]), m) for r in range(world)], world)
+        cut_values, cut_ties = thresholds_for_rank(values, split_rank, split_pos, rank)     # this rank's own cuts
 
         bits = max(1, (world - 1).bit_length())
-        route = ops.route(keys, thresholds)
+        route = ops.route(keys, cut_values, cut_ties)
         hist = ops.histogram(route, 0, bits)
         counts = hist.to(torch.int64) & 0xFFFFFFFF
         allc = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
@@ -392,7 +425,7 @@ class ShardedSorter:
         owner = np.minimum(np.arange(1 << bits), world - 1)
         plan = plan_exchange(counts_all, rank, owner=owner)
         plan["narrow_bits"] = 0
-        plan["value_thresholds"] = thresholds
+        plan["value_thresholds"] = (cut_values, cut_ties)
         total = int(plan["totals"].sum())
         plan["imbalance"] = float(plan["totals"].max()) * world / max(total, 1)
         self.last_plan = plan

@@ -144,11 +144,14 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
                         const uint64_t *d_bin_dst, void *d_temp, size_t temp_bytes,
                         void *stream);
 
-/* d_route[i] = number of thresholds <= d_keys[i], for `count` (<= 255) non-decreasing 64-bit
- * thresholds in [0, 2^32]: the destination shard of every key under VALUE splitters.  Used by
- * the multi-GPU drivers when the bin-edge splitters of the partition byte leave the shards
- * unbalanced (skewed keys): the route array is then the key of a digit pass
- * (b200sort_digit_pass, shift 0) that carries the real keys as values to their owners.
+/* d_route[i] = number of cuts j with (value_j, tie_j) <= (d_keys[i], i) in lexicographic order:
+ * the destination shard of every key under VALUE splitters.  d_thresholds holds `count` (<= 255)
+ * values in [0, 2^32] followed by `count` tie indices; a key equal to value_j is at or above cut
+ * j from local index tie_j on (tie 0: the whole run of equal keys goes right; tie >= n: left).
+ * Cuts must be non-decreasing.  Used by the multi-GPU drivers when the bin-edge splitters of the
+ * partition byte leave the shards unbalanced (skewed keys): the route array is then the key of a
+ * digit pass (b200sort_digit_pass, shift 0) that carries the real keys as values to their
+ * owners; the tie index cuts a run of equal keys at a position, which keeps ties in input order.
  * No counterpart in the reference (single GPU). */
 int b200sort_route(const uint32_t *d_keys, uint64_t n, const uint64_t *d_thresholds, int count,
                    uint32_t *d_route, void *stream);

@@ -72,6 +72,16 @@ def test_narrow_partition_detection():
     assert np.array_equal(p["src_base"], uniform[:2].reshape(2, 4, 64).sum(axis=2).sum(axis=0))
 
 
+def _route_np(keys, values, ties):
+    """b200sort_route on the host: #{j : (values[j], ties[j]) <= (key, index)}."""
+    k = keys.astype(np.int64)
+    i = np.arange(k.size, dtype=np.int64)
+    dest = np.zeros(k.size, dtype=np.int64)
+    for v, c in zip(values, ties):
+        dest += (k > int(v)) | ((k == int(v)) & (i >= int(c)))
+    return dest
+
+
 class NumpyOps:
     """numpy stand-ins for the device kernels (same contracts as include/b200sort.h)."""
 
@@ -99,10 +109,8 @@ class NumpyOps:
         out_vals.numpy().view(np.uint32)[:] = vo
         return out, out_vals
 
-    def route(self, keys, thresholds):
-        k = keys.numpy().view(np.uint32).astype(np.int64)
-        r = np.searchsorted(np.asarray(thresholds, dtype=np.int64), k, side="right")
-        return torch.from_numpy(r.astype(np.int32))
+    def route(self, keys, values, ties):
+        return torch.from_numpy(_route_np(keys.numpy().view(np.uint32), values, ties).astype(np.int32))
 
     def sample(self, keys, idx):
         return keys[torch.from_numpy(idx)]
@@ -122,6 +130,10 @@ def _make(O, kind, count, first, total):
     """small16 / small8: uniform keys with constant (zero) high bytes -- the partition digit must move down.
     A "vs:" prefix only changes the sorter (value splitters forced), not the data."""
     kind = kind.split(":")[-1]
+    if kind == "heavyvalue":    # 70 % of the keys are ONE value: its run must be split between the ranks
+        k = O.generate("uniform", count, first=first, total=total)
+        heavy = (O.generate("uniform", count, first=first + total, total=2 * total) % np.uint32(10)) < 7
+        return np.where(heavy, np.uint32(0x5A5A5A5A), k)
     if kind == "heavybin":      # 90 % of the keys share one top byte but differ below it
         k = O.generate("uniform", count, first=first, total=total)
         heavy = (O.generate("uniform", count, first=first + total, total=2 * total) % np.uint32(10)) != 0
@@ -179,7 +191,7 @@ def _free_port():
 @pytest.mark.parametrize("kind,n_total", [("uniform", 200003), ("zipf", 120001), ("all_equal", 5000),
                                           ("sorted", 70000), ("small16", 90001), ("small8", 30000),
                                           ("heavybin", 150001), ("vs:uniform", 100003), ("vs:zipf", 90001),
-                                          ("vs:unique16", 60000), ("vs:sorted", 50001)])
+                                          ("vs:unique16", 60000), ("vs:sorted", 50001), ("heavyvalue", 80001)])
 def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     import oracle as O
     world = 2
@@ -192,9 +204,11 @@ def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     assert all(f[1] for f in flags), "verify_sharded accepted a corrupted result"
     if kind in ("uniform", "small16", "small8", "all_equal", "heavybin", "vs:uniform", "vs:sorted"):
         assert abs(len(shards[0]) - len(shards[1])) < 0.03 * n_total + 2          # balanced split
+    if kind == "heavyvalue":   # the run of the heavy value is cut at a position: not the 10.6 % / 89.4 % of an unsplit run
+        assert abs(len(shards[0]) - len(shards[1])) < 0.03 * n_total
     expected_shift = {"small16": 8, "small8": 0, "all_equal": 0}.get(kind, 24)
     assert all(int(f[2]) == expected_shift for f in flags)                        # partition digit moved down
-    if kind.startswith("vs:") or kind == "heavybin":
+    if kind.startswith("vs:") or kind in ("heavybin", "heavyvalue"):
         assert all(int(f[3]) for f in flags), "value splitters were expected for the keys sort"
     # pairs: concatenation == stable sort of (masked key, global index)
     pk = np.concatenate([np.load(tmp_path / f"pairs_k{r}.npy") for r in range(world)])
@@ -204,24 +218,48 @@ def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     assert np.array_equal(pk, rk) and np.array_equal(pv, rv)
 
 
-def test_value_thresholds_and_sample_indices():
+def _route_all(shards, world, m=2048):
+    """Host model of the value-splitter plan: returns per-shard destination arrays."""
+    positions = [mgpu.sample_indices(sh.size, m) for sh in shards]
+    samples = [sh[p] if sh.size else np.zeros(0, np.uint32) for sh, p in zip(shards, positions)]
+    pool = np.sort(np.concatenate(samples))
+    values, split_rank, split_pos = mgpu.value_splitters(pool, samples, positions, world)
+    dests = []
+    for r, sh in enumerate(shards):
+        v, c = mgpu.thresholds_for_rank(values, split_rank, split_pos, r)
+        assert np.all(np.diff(v) >= 0)
+        dests.append(_route_np(sh, v, c))
+    return dests
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_value_splitters_give_a_stable_balanced_range_partition(world):
     rng = np.random.default_rng(5)
-    s = np.sort(rng.integers(0, 1 << 32, 4096, dtype=np.uint64))
-    for world in (2, 3, 4, 8):
-        t = mgpu.value_thresholds(s, world)
-        assert t.shape == (world - 1,) and np.all(np.diff(t) >= 0)
-        shares = np.bincount(np.searchsorted(t, s.astype(np.int64), side="right"), minlength=world)
-        assert shares.max() - shares.min() <= 2
-    # runs of equal values are never split; the cut goes to the nearer end of the run
-    s = np.sort(np.repeat(np.array([5, 9, 2 ** 32 - 1], dtype=np.uint64), [700, 200, 100]))
-    t = mgpu.value_thresholds(s, 4)
-    assert list(t) == [5, 6, 9] or list(t) == [5, 6, 6] or np.all(np.isin(t, [5, 6, 9, 10, 2 ** 32 - 1, 2 ** 32]))
-    dest = np.searchsorted(t, s.astype(np.int64), side="right")
-    for v in (5, 9, 2 ** 32 - 1):
-        assert len(set(dest[s == v])) == 1
-    assert mgpu.value_thresholds(np.full(64, 2 ** 32 - 1, dtype=np.uint64), 2)[0] in (2 ** 32 - 1, 2 ** 32)
-    assert mgpu.value_thresholds(np.zeros(0, dtype=np.uint64), 4).shape == (3,)
+    n = 40000
+    cases = {
+        "uniform": rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32),
+        "all_equal": np.full(n, 0xDEADBEEF, dtype=np.uint32),
+        "max_value": np.full(n, 0xFFFFFFFF, dtype=np.uint32),
+        "two_values": rng.integers(0, 2, n).astype(np.uint32) * np.uint32(77),
+        "heavy_head": np.where(rng.random(n) < 0.6, np.uint32(123456), rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)),
+        "sixteen": (rng.integers(0, 16, n).astype(np.uint32) * np.uint32(0x01010101)),
+    }
+    for name, keys in cases.items():
+        shards = np.array_split(keys, world)
+        dests = _route_all(shards, world)
+        dest = np.concatenate(dests)
+        # a range partition: destinations are monotone in the key ...
+        order = np.argsort(keys, kind="stable")
+        assert np.all(np.diff(dest[order]) >= 0), name
+        # ... which for equal keys means monotone in the global index (the stable order)
+        shares = np.bincount(dest, minlength=world)
+        assert shares.max() <= 1.10 * n / world + 64, (name, world, shares)      # sampling noise only
+
+
+def test_sample_indices():
     for n_local in (1, 7, 8192, 8193, 10 ** 6 + 3):
         idx = mgpu.sample_indices(n_local, 8192)
         assert idx.size == 8192 and idx.min() >= 0 and idx.max() < n_local and np.all(np.diff(idx) >= 0)
     assert mgpu.sample_indices(0).size == 0
+    v, r, c = mgpu.value_splitters(np.zeros(0, np.uint32), [np.zeros(0, np.uint32)] * 4, [np.zeros(0, np.int64)] * 4, 4)
+    assert v.shape == (3,) and r.shape == (3,) and c.shape == (3,)

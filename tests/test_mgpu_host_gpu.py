@@ -163,3 +163,22 @@ def test_value_splitters_keep_pairs_stable(rs, oracle):
         rs.sort_pairs_by_devices(k, v, n, ok, ov, 8, 512, devs)
         assert rs.mgpu_last_stats()["value_splitters"] == 1
         assert np.array_equal(ok, wk) and np.array_equal(ov, wv), devs
+
+
+def test_one_heavy_value_is_split_between_shards_by_source_order(rs, oracle):
+    n = (1 << 21) + 3
+    k = oracle.generate("uniform", n)
+    heavy = (oracle.generate("uniform", n, first=n, total=2 * n) % np.uint32(10)) < 7
+    k = np.where(heavy, np.uint32(0x5A5A5A5A), k).astype(np.uint32)          # 70 % of the keys are one value
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v, 8)
+    for devs in ([0, 0, 0, 0], [0] * 8) + tuple(d for d in device_sets() if len(set(d)) > 1):
+        ok, ov = np.zeros_like(k), np.zeros_like(v)
+        rs.sort_pairs_by_devices(k, v, n, ok, ov, 8, 512, list(devs))
+        st = rs.mgpu_last_stats()
+        assert np.array_equal(ok, wk) and np.array_equal(ov, wv), devs      # ties still in input order
+        assert st["value_splitters"] == 1 and st["imbalance"] < 1.06, (devs, st)   # the run is cut at a position
+    # all keys equal: every shard keeps its own keys
+    kk = np.full(n, 7, dtype=np.uint32)
+    assert np.array_equal(run(rs, kk, 8, [0, 0, 0, 0]), kk)
+    assert rs.mgpu_last_stats()["imbalance"] < 1.01

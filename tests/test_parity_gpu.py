@@ -407,6 +407,12 @@ def test_route_counts_thresholds_below_or_equal(rs, oracle):
         got = to_host(rs.route(to_dev(k), thresholds))
         want = np.searchsorted(np.asarray(thresholds, dtype=np.int64), k.astype(np.int64), side="right")
         assert np.array_equal(got, want.astype(np.uint32)), thresholds[:4]
+    # tie indices: a key equal to a cut value is at or above the cut from that local index on
+    dup = np.repeat(np.array([3, 9, 9, 9, 20], dtype=np.uint32), 1000)
+    idx = np.arange(dup.size)
+    got = to_host(rs.route(to_dev(dup), [9, 9, 20], [1500, 3200, 1 << 62]))
+    want = (dup > 9).astype(np.uint32) * 2 + ((dup == 9) & (idx >= 1500)) + ((dup == 9) & (idx >= 3200))
+    assert np.array_equal(got, want.astype(np.uint32))
     # route as the key of a digit pass that carries the real keys: a stable partition by value range
     t = [1 << 30, 1 << 31, 3 << 30]
     r = rs.route(to_dev(k), t)

@@ -27,7 +27,7 @@ def main():
     report = {"world": world}
     for fused in (False, True):
         for kind, log2n in (("uniform", 24), ("zipf", 22), ("unique16", 20), ("all_equal", 18), ("iota", 20),
-                            ("heavybin", 22)):
+                            ("heavybin", 22), ("heavyvalue", 22)):
             total = (1 << log2n) + 12345
             per = total // world
             first = rank * per
@@ -38,6 +38,11 @@ def main():
                 pick = rs.generate("uniform", count, first=first + total, total=2 * total)
                 heavy = torch.remainder(pick.to(torch.int64) & 0xFFFFFFFF, 10) != 0
                 keys = torch.where(heavy, (keys & 0x00FFFFFF) | 0x5A000000, keys)
+            elif kind == "heavyvalue":   # 70 % of the keys are ONE value: its run is cut between ranks at a position
+                keys = rs.generate("uniform", count, first=first, total=total)
+                pick = rs.generate("uniform", count, first=first + total, total=2 * total)
+                heavy = torch.remainder(pick.to(torch.int64) & 0xFFFFFFFF, 10) < 7
+                keys = torch.where(heavy, torch.full_like(keys, 0x5A5A5A5A), keys)
             else:
                 keys = rs.generate(kind, count, first=first, total=total, zipf_cdf=cdf)
             sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=total + 1024, nbits=8, fused=fused)
