@@ -344,7 +344,8 @@ def run_multi(args):
     vals = torch.arange(rank * per, (rank + 1) * per, dtype=torch.int64, device="cuda").to(torch.int32) if pairs else None
     slack = 1.02 if kind == "uniform" else 1.6      # skewed keys: value splitters never split one value
     sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * slack) + (1 << 20),
-                                nbits=args.nbits, fused=not args.no_fused, allow_narrow=not args.no_narrow)
+                                nbits=args.nbits, fused=not args.no_fused, allow_narrow=not args.no_narrow,
+                                balance_threshold=args.balance_threshold)
 
     def sort_once():
         return sorter.sort(keys) if not pairs else sorter.sort_pairs(keys, vals)[0]
@@ -428,6 +429,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--balance-threshold", type=float, default=1.2,
+                    help="multi-GPU: bin-edge splitters leaving a shard above this x mean switch to value splitters")
     ap.add_argument("--workload", default="uniform",
                     choices=["uniform", "zipf", "unique16", "all_equal", "sorted", "reversed", "pairs"])
     ap.add_argument("--log2n", type=int, default=28)

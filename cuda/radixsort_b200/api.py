@@ -293,11 +293,12 @@ def digit_pass(keys, shift: int, bits: int, vals=None, out_keys=None, out_vals=N
     return (out_keys, out_vals) if vals is not None else out_keys
 
 
-def route(keys, values, ties=None, out=None, stream=None):
+def route(keys, values, ties=None, out=None, stream=None, with_counts: bool = False):
     """out[i] = #{j : (values[j], ties[j]) <= (keys[i], i)} (unsigned keys, lexicographic): b200sort_route.
 
     ``values``: non-decreasing integers in [0, 2^32]; ``ties``: for each cut the local index from
-    which a key EQUAL to the value counts as at-or-above the cut (default 0: the whole run)."""
+    which a key EQUAL to the value counts as at-or-above the cut (default 0: the whole run).
+    ``with_counts``: also return the number of keys per destination (int32 tensor, len(values)+1)."""
     torch = _torch()
     values = [int(v) for v in values]
     ties = [0] * len(values) if ties is None else [int(t) for t in ties]
@@ -305,10 +306,12 @@ def route(keys, values, ties=None, out=None, stream=None):
         raise ValueError("values and ties differ in length")
     table = torch.tensor(values + ties, dtype=torch.int64, device=keys.device)
     out = torch.empty_like(keys) if out is None else out
+    counts = torch.empty(len(values) + 1, dtype=torch.int32, device=keys.device) if with_counts else None
     _lib.check(_lib.load().b200sort_route(_dev_ptr(keys, "keys"), keys.numel(),
                                           table.data_ptr() if table.numel() else None,
-                                          len(values), _dev_ptr(out, "out"), _stream_ptr(stream)))
-    return out
+                                          len(values), _dev_ptr(out, "out"),
+                                          counts.data_ptr() if with_counts else None, _stream_ptr(stream)))
+    return (out, counts) if with_counts else out
 
 
 def exclusive_scan(x, out=None, workspace: Workspace | None = None, stream=None):

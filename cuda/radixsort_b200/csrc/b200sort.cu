@@ -764,15 +764,20 @@ int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind,
 }
 
 int b200sort_route(const uint32_t *d_keys, uint64_t n, const uint64_t *d_thresholds, int count, uint32_t *d_route,
-                   void *stream) {
+                   uint32_t *d_counts, void *stream) {
     if (count < 0 || count > kMaxRouteThresholds) return fail(B200SORT_EINVAL, "threshold count");
     if (n > 0 && (!d_keys || !d_route || (count > 0 && !d_thresholds))) return fail(B200SORT_EINVAL, "null buffer");
-    if (n == 0) return 0;
     int rc = check_device();
     if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_counts) CU(cudaMemsetAsync(d_counts, 0, (size_t)(count + 1) * sizeof(uint32_t), s));
+    if (n == 0) return 0;
     const uint64_t want = (n + 256ull * 8 - 1) / (256ull * 8);
     const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)g_num_sms * 8);
-    route_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, n, d_thresholds, count, d_route);
+    if (count <= kRouteRegCuts)
+        route_kernel<true><<<grid, 256, 0, s>>>(d_keys, n, d_thresholds, count, d_route, d_counts);
+    else
+        route_kernel<false><<<grid, 256, 0, s>>>(d_keys, n, d_thresholds, count, d_route, d_counts);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(cudaGetLastError());
     return 0;

@@ -428,17 +428,15 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
             uint64_t *d_thr = reinterpret_cast<uint64_t *>(static_cast<char *>(s.small.p) + 6144);
             std::copy(thresholds.begin(), thresholds.end(), s.h_bin_dst);  // pinned scratch, re-filled below
             CU(cudaMemcpyAsync(d_thr, s.h_bin_dst, thresholds.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+            uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);  // G destination counts, tallied by the route kernel
             RC(b200sort_route(static_cast<const uint32_t *>(s.in_k.p), s.count, d_thr, (int)(thresholds.size() / 2),
-                              static_cast<uint32_t *>(s.route.p), s.stream));
-            uint32_t *d_hist = static_cast<uint32_t *>(s.small.p);
-            RC(b200sort_histogram(static_cast<const uint32_t *>(s.route.p), s.count, 0, part_bits, d_hist, s.temp.p,
-                                  s.temp.bytes, s.stream));
-            CU(cudaMemcpyAsync(s.h_counts, d_hist, bins * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+                              static_cast<uint32_t *>(s.route.p), d_hist, s.stream));
+            CU(cudaMemcpyAsync(s.h_counts, d_hist, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         }
         RC(sync_all(sh));
         counts.assign((size_t)G * bins, 0);
         for (int i = 0; i < G; ++i)
-            for (int b = 0; b < bins; ++b) counts[(size_t)i * bins + b] = sh[i].h_counts[b];
+            for (int b = 0; b < G; ++b) counts[(size_t)i * bins + b] = sh[i].h_counts[b];
         owner.assign(bins, 0);
         for (int b = 0; b < bins; ++b) owner[b] = std::min(b, G - 1);
         max_recv = fill_matrix();

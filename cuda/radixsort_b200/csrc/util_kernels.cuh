@@ -84,21 +84,43 @@ __global__ void __launch_bounds__(256) verify_kernel(const uint32_t *__restrict_
 // run of equal keys be cut at a position, in input order.  Cuts must be non-decreasing.
 // The result is then used as the KEY of a digit pass that carries the real keys as values.
 constexpr int kMaxRouteThresholds = 255;
+constexpr int kRouteRegCuts = 8;  // up to this many cuts live in registers (2..9 shards)
+
+// counts (may be null): counts[d] += number of keys routed to d, d in [0, count].
+template <bool SMALL>
 __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__ keys, uint64_t n,
                                                     const uint64_t *__restrict__ thresholds, int count,
-                                                    uint32_t *__restrict__ route) {
-    __shared__ uint64_t s_v[kMaxRouteThresholds + 1];
-    __shared__ uint64_t s_c[kMaxRouteThresholds + 1];
-    for (int j = threadIdx.x; j < count; j += blockDim.x) {
-        s_v[j] = thresholds[j];
-        s_c[j] = thresholds[count + j];
+                                                    uint32_t *__restrict__ route, uint32_t *__restrict__ counts) {
+    __shared__ uint64_t s_v[SMALL ? 1 : kMaxRouteThresholds + 1];
+    __shared__ uint64_t s_c[SMALL ? 1 : kMaxRouteThresholds + 1];
+    __shared__ uint32_t s_hist[SMALL ? kRouteRegCuts + 1 : kMaxRouteThresholds + 1];
+    uint64_t v[SMALL ? kRouteRegCuts : 1], c[SMALL ? kRouteRegCuts : 1];
+    uint32_t mine[SMALL ? kRouteRegCuts + 1 : 1];  // per-lane tallies (SMALL)
+    if constexpr (SMALL) {
+#pragma unroll
+        for (int j = 0; j < kRouteRegCuts; ++j) {  // unused cuts sit above every (key, index)
+            v[j] = j < count ? thresholds[j] : ~0ull;
+            c[j] = j < count ? thresholds[count + j] : ~0ull;
+        }
+#pragma unroll
+        for (int d = 0; d <= kRouteRegCuts; ++d) mine[d] = 0;
+        if (threadIdx.x <= kRouteRegCuts) s_hist[threadIdx.x] = 0;
+    } else {
+        for (int j = threadIdx.x; j < count; j += blockDim.x) {
+            s_v[j] = thresholds[j];
+            s_c[j] = thresholds[count + j];
+        }
+        for (int j = threadIdx.x; j <= count; j += blockDim.x) s_hist[j] = 0;
     }
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t k = keys[i];
         uint32_t r = 0;
-        if (count <= 8) {
-            for (int j = 0; j < count; ++j) r += (s_v[j] < k || (s_v[j] == k && s_c[j] <= i)) ? 1u : 0u;
+        if constexpr (SMALL) {
+#pragma unroll
+            for (int j = 0; j < kRouteRegCuts; ++j) r += (v[j] < k || (v[j] == k && c[j] <= i)) ? 1u : 0u;
+#pragma unroll
+            for (int d = 0; d <= kRouteRegCuts; ++d) mine[d] += (r == (uint32_t)d) ? 1u : 0u;
         } else {  // upper bound by bisection
             int lo = 0, hi = count;
             while (lo < hi) {
@@ -106,9 +128,21 @@ __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__
                 if (s_v[mid] < k || (s_v[mid] == k && s_c[mid] <= i)) lo = mid + 1; else hi = mid;
             }
             r = (uint32_t)lo;
+            if (counts) atomicAdd(&s_hist[r], 1u);
         }
         route[i] = r;
     }
+    if (!counts) return;
+    if constexpr (SMALL) {
+#pragma unroll
+        for (int d = 0; d <= kRouteRegCuts; ++d) {
+            const uint32_t w = __reduce_add_sync(0xffffffffu, mine[d]);
+            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[d], w);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d <= count; d += blockDim.x)
+        if (s_hist[d]) atomicAdd(&counts[d], s_hist[d]);
 }
 
 // Probe for the fused exchange: copies n uint32 from src to dst (dst may be peer memory) with

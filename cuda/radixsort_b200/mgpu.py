@@ -99,16 +99,25 @@ def plan_exchange(counts_all: np.ndarray, rank: int, owner=None):
 SAMPLE_PER_RANK = 8192
 
 
+_sample_cache: dict = {}
+
+
 def sample_indices(n_local: int, m: int = SAMPLE_PER_RANK) -> np.ndarray:
     """m positions spread over a shard: one per stride, at a position inside the stride that
     changes from sample to sample (so periodic inputs do not alias with the stride)."""
     if n_local <= 0:
         return np.zeros(0, dtype=np.int64)
+    hit = _sample_cache.get((n_local, m))
+    if hit is not None:
+        return hit
     i = np.arange(m, dtype=np.int64)
     base = (i * n_local) // m
     stride = max(n_local // m, 1)
     jitter = ((i * 2654435761) & 0xFFFFFFFF) % stride
-    return np.minimum(base + jitter, n_local - 1)
+    out = np.minimum(base + jitter, n_local - 1)
+    if len(_sample_cache) < 64:
+        _sample_cache[(n_local, m)] = out
+    return out
 
 
 TIE_ALL_LEFT = 1 << 62   # tie index beyond any shard: every key equal to the cut value stays left of the cut
@@ -133,7 +142,7 @@ def value_splitters(sorted_pool: np.ndarray, samples_by_rank, positions_by_rank,
     split_pos = np.zeros(max(world - 1, 0), dtype=np.int64)
     if m == 0:
         return values, split_rank, split_pos
-    per_rank = [np.asarray(x).astype(np.int64) for x in samples_by_rank]
+    per_rank = [np.asarray(x) for x in samples_by_rank]
     for j in range(1, world):
         q = min((j * m) // world, m - 1)
         v = int(s[q])
@@ -141,6 +150,9 @@ def value_splitters(sorted_pool: np.ndarray, samples_by_rank, positions_by_rank,
         left = q - lo                                           # sampled copies of v that belong left of the cut
         values[j - 1] = v
         split_rank[j - 1] = world                                # default: the whole run goes left
+        if left == 0:                                            # the cut sits at the start of the run: all of it goes right
+            split_rank[j - 1] = 0
+            continue
         for r in range(world):
             hits = np.flatnonzero(per_rank[r] == v)
             if left < hits.size:
@@ -181,7 +193,7 @@ class DeviceOps:
         return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws)
 
     def route(self, keys, values, ties):
-        return self.api.route(keys, values, ties)
+        return self.api.route(keys, values, ties, with_counts=True)
 
     def sample(self, keys, idx):
         return keys[torch.from_numpy(idx).to(keys.device)]
@@ -416,12 +428,12 @@ class ShardedSorter:
         cut_values, cut_ties = thresholds_for_rank(values, split_rank, split_pos, rank)     # this rank's own cuts
 
         bits = max(1, (world - 1).bit_length())
-        route = ops.route(keys, cut_values, cut_ties)
-        hist = ops.histogram(route, 0, bits)
-        counts = hist.to(torch.int64) & 0xFFFFFFFF
+        route, dest_counts = ops.route(keys, cut_values, cut_ties)      # destinations + how many keys go to each
+        counts = dest_counts.to(torch.int64) & 0xFFFFFFFF
         allc = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
         dist.all_gather_into_tensor(allc, counts, group=self.group)
-        counts_all = allc.cpu().numpy().reshape(world, -1)
+        counts_all = np.zeros((world, 1 << bits), dtype=np.int64)      # bins >= world stay empty
+        counts_all[:, :world] = allc.cpu().numpy().reshape(world, world)
         owner = np.minimum(np.arange(1 << bits), world - 1)
         plan = plan_exchange(counts_all, rank, owner=owner)
         plan["narrow_bits"] = 0

@@ -152,9 +152,11 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
  * partition byte leave the shards unbalanced (skewed keys): the route array is then the key of a
  * digit pass (b200sort_digit_pass, shift 0) that carries the real keys as values to their
  * owners; the tie index cuts a run of equal keys at a position, which keeps ties in input order.
+ * d_counts (may be NULL): count+1 uint32, overwritten with the number of keys routed to each
+ * destination -- the row of the exchange matrix this shard contributes.
  * No counterpart in the reference (single GPU). */
 int b200sort_route(const uint32_t *d_keys, uint64_t n, const uint64_t *d_thresholds, int count,
-                   uint32_t *d_route, void *stream);
+                   uint32_t *d_route, uint32_t *d_counts, void *stream);
 
 /* Device-wide exclusive prefix sum of uint32 (mod 2^32), one pass, decoupled look-back.  The
  * public form of the reference's scan stage: scan() + scanBlocks + addScannedBlockSumsToScannedBlocks

@@ -110,7 +110,9 @@ class NumpyOps:
         return out, out_vals
 
     def route(self, keys, values, ties):
-        return torch.from_numpy(_route_np(keys.numpy().view(np.uint32), values, ties).astype(np.int32))
+        dest = _route_np(keys.numpy().view(np.uint32), values, ties)
+        counts = np.bincount(dest, minlength=len(values) + 1)
+        return torch.from_numpy(dest.astype(np.int32)), torch.from_numpy(counts.astype(np.int32))
 
     def sample(self, keys, idx):
         return keys[torch.from_numpy(idx)]

@@ -404,9 +404,11 @@ def test_route_counts_thresholds_below_or_equal(rs, oracle):
     for thresholds in ([], [0], [1 << 32], [0x80000000], [5, 5, 1 << 31, (1 << 32) - 1, 1 << 32],
                        sorted(int(x) for x in rng.integers(0, 1 << 32, 7, dtype=np.uint64)),
                        sorted(int(x) for x in rng.integers(0, 1 << 32, 200, dtype=np.uint64))):
-        got = to_host(rs.route(to_dev(k), thresholds))
+        got, counts = rs.route(to_dev(k), thresholds, with_counts=True)
+        got = to_host(got)
         want = np.searchsorted(np.asarray(thresholds, dtype=np.int64), k.astype(np.int64), side="right")
         assert np.array_equal(got, want.astype(np.uint32)), thresholds[:4]
+        assert np.array_equal(to_host(counts), np.bincount(want, minlength=len(thresholds) + 1).astype(np.uint32))
     # tie indices: a key equal to a cut value is at or above the cut from that local index on
     dup = np.repeat(np.array([3, 9, 9, 9, 20], dtype=np.uint32), 1000)
     idx = np.arange(dup.size)
