@@ -196,7 +196,10 @@ class DeviceOps:
         return self.api.route(keys, values, ties, with_counts=True)
 
     def sample(self, keys, idx):
-        return keys[torch.from_numpy(idx).to(keys.device)]
+        key = (keys.numel(), idx.size)
+        if getattr(self, "_sample_key", None) != key:       # positions depend on the shard size only
+            self._sample_key, self._sample_idx = key, torch.from_numpy(idx).to(keys.device)
+        return keys[self._sample_idx]
 
     def empty(self, n):
         return torch.empty(n, dtype=torch.int32, device="cuda")
@@ -418,17 +421,20 @@ class ShardedSorter:
         gathered = ops.empty(world * m)
         dist.all_gather_into_tensor(gathered, mine.contiguous(), group=self.group)
         valid = [r for r in range(world) if int(shard_sizes[r]) > 0]
-        pool = torch.cat([gathered[r * m:(r + 1) * m] for r in valid])
+        pool = gathered if len(valid) == world else torch.cat([gathered[r * m:(r + 1) * m] for r in valid])
         pool_sorted = ops.sort(pool, 8, ops.empty(pool.numel()))
+        t.mark("splitters:sample")
         by_rank = gathered.cpu().numpy().view(np.uint32).reshape(world, m)
         empty = np.zeros(0, dtype=np.uint32)
         values, split_rank, split_pos = value_splitters(
             pool_sorted.cpu().numpy().view(np.uint32), [by_rank[r] if r in valid else empty for r in range(world)],
             [sample_indices(int(shard_sizes[r]), m) for r in range(world)], world)
         cut_values, cut_ties = thresholds_for_rank(values, split_rank, split_pos, rank)     # this rank's own cuts
+        t.mark("splitters:cuts")
 
         bits = max(1, (world - 1).bit_length())
         route, dest_counts = ops.route(keys, cut_values, cut_ties)      # destinations + how many keys go to each
+        t.mark("splitters:route")
         counts = dest_counts.to(torch.int64) & 0xFFFFFFFF
         allc = torch.empty(world * counts.numel(), dtype=torch.int64, device=counts.device)
         dist.all_gather_into_tensor(allc, counts, group=self.group)
