@@ -94,16 +94,18 @@ __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__
     __shared__ uint64_t s_v[SMALL ? 1 : kMaxRouteThresholds + 1];
     __shared__ uint64_t s_c[SMALL ? 1 : kMaxRouteThresholds + 1];
     __shared__ uint32_t s_hist[SMALL ? kRouteRegCuts + 1 : kMaxRouteThresholds + 1];
-    uint64_t v[SMALL ? kRouteRegCuts : 1], c[SMALL ? kRouteRegCuts : 1];
-    uint32_t mine[SMALL ? kRouteRegCuts + 1 : 1];  // per-lane tallies (SMALL)
+    // SMALL: cuts in registers as (32-bit value, tie index); a value of 2^32 ("nothing is at or
+    // above") becomes (0xFFFFFFFF, never).  above[j] = keys of this lane at or above cut j.
+    uint32_t v[SMALL ? kRouteRegCuts : 1], above[SMALL ? kRouteRegCuts : 1], seen = 0;
+    uint64_t c[SMALL ? kRouteRegCuts : 1];
     if constexpr (SMALL) {
 #pragma unroll
-        for (int j = 0; j < kRouteRegCuts; ++j) {  // unused cuts sit above every (key, index)
-            v[j] = j < count ? thresholds[j] : ~0ull;
-            c[j] = j < count ? thresholds[count + j] : ~0ull;
+        for (int j = 0; j < kRouteRegCuts; ++j) {
+            const uint64_t value = j < count ? thresholds[j] : ~0ull;
+            v[j] = value > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)value;
+            c[j] = value > 0xFFFFFFFFull ? ~0ull : thresholds[count + j];
+            above[j] = 0;
         }
-#pragma unroll
-        for (int d = 0; d <= kRouteRegCuts; ++d) mine[d] = 0;
         if (threadIdx.x <= kRouteRegCuts) s_hist[threadIdx.x] = 0;
     } else {
         for (int j = threadIdx.x; j < count; j += blockDim.x) {
@@ -114,14 +116,19 @@ __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__
     }
     __syncthreads();
     auto dest = [&](uint32_t key, uint64_t i) -> uint32_t {
-        const uint64_t k = key;
         uint32_t r = 0;
         if constexpr (SMALL) {
+            ++seen;
 #pragma unroll
-            for (int j = 0; j < kRouteRegCuts; ++j) r += (v[j] < k || (v[j] == k && c[j] <= i)) ? 1u : 0u;
-#pragma unroll
-            for (int d = 0; d <= kRouteRegCuts; ++d) mine[d] += (r == (uint32_t)d) ? 1u : 0u;
+            for (int j = 0; j < kRouteRegCuts; ++j) {
+                if (j >= count) break;  // uniform
+                uint32_t ge = key > v[j] ? 1u : 0u;
+                if (key == v[j]) ge = c[j] <= i ? 1u : 0u;
+                r += ge;
+                above[j] += ge;
+            }
         } else {  // upper bound by bisection
+            const uint64_t k = key;
             int lo = 0, hi = count;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -151,10 +158,14 @@ __global__ void __launch_bounds__(256) route_kernel(const uint32_t *__restrict__
     for (uint64_t i = 4 * n4 + gtid; i < n; i += gsize) route[i] = dest(keys[i], i);
     if (!counts) return;
     if constexpr (SMALL) {
+        // cuts are non-decreasing, so keys routed to d = (keys at or above cut d-1) - (at or above cut d)
+        uint32_t prev = __reduce_add_sync(0xffffffffu, seen);
 #pragma unroll
         for (int d = 0; d <= kRouteRegCuts; ++d) {
-            const uint32_t w = __reduce_add_sync(0xffffffffu, mine[d]);
-            if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_hist[d], w);
+            if (d > count) break;
+            const uint32_t next = d < count ? __reduce_add_sync(0xffffffffu, above[d < kRouteRegCuts ? d : 0]) : 0u;
+            if ((threadIdx.x & 31) == 0 && prev != next) atomicAdd(&s_hist[d], prev - next);
+            prev = next;
         }
     }
     __syncthreads();
