@@ -220,6 +220,27 @@ def test_sharded_sort_world2_gloo(tmp_path, kind, n_total):
     assert np.array_equal(pk, rk) and np.array_equal(pv, rv)
 
 
+@pytest.mark.parametrize("world,kind,n_total", [(4, "uniform", 160003), (4, "vs:zipf", 100001), (4, "heavyvalue", 120001),
+                                                (3, "small16", 90002), (3, "heavybin", 90001)])
+def test_sharded_sort_more_ranks_gloo(tmp_path, world, kind, n_total):
+    """Same check with 3 ranks (no narrow partition: not a power of two) and 4 ranks."""
+    import oracle as O
+    mp.spawn(_worker, args=(world, _free_port(), kind, n_total, str(tmp_path)), nprocs=world, join=True)
+    shards = [np.load(tmp_path / f"shard{r}.npy") for r in range(world)]
+    flags = [np.load(tmp_path / f"flags{r}.npy") for r in range(world)]
+    whole = _make(O, kind, n_total, 0, n_total)
+    assert np.array_equal(np.concatenate(shards), O.sort_keys(whole, 8))
+    assert all(f[0] for f in flags) and all(f[1] for f in flags)
+    sizes = np.array([len(x) for x in shards])
+    assert sizes.max() < 1.12 * n_total / world + 64, sizes                     # every kind here must end up balanced
+    if kind != "uniform" and kind != "small16":
+        assert all(int(f[3]) for f in flags), "value splitters were expected"
+    pk = np.concatenate([np.load(tmp_path / f"pairs_k{r}.npy") for r in range(world)])
+    pv = np.concatenate([np.load(tmp_path / f"pairs_v{r}.npy") for r in range(world)])
+    rk, rv = O.sort_pairs(whole & np.uint32(0xFF0000FF), np.arange(n_total, dtype=np.uint32), 8)
+    assert np.array_equal(pk, rk) and np.array_equal(pv, rv)
+
+
 def _route_all(shards, world, m=2048):
     """Host model of the value-splitter plan: returns per-shard destination arrays."""
     positions = [mgpu.sample_indices(sh.size, m) for sh in shards]
