@@ -41,6 +41,9 @@ SIGNATURES = {
                                            C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "b200sort_mgpu_last_stats": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "b200sort_mgpu_shutdown": (C.c_int, []),
+    "b200sort_plan_owners": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200sort_plan_value_cuts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
     "b200sort_temp_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
     "b200sort_keys": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                 C.c_void_p]),

@@ -310,7 +310,8 @@ ValueCuts value_splitters(const std::vector<uint32_t> &pool_sorted, const std::v
         const size_t lo = std::lower_bound(pool_sorted.begin(), pool_sorted.end(), v) - pool_sorted.begin();
         size_t left = q - lo;  // sampled copies of v that belong left of the cut
         c.value[j - 1] = v;
-        c.split[j - 1] = G;    // default: the whole run goes left
+        if (left == 0) continue;  // the cut sits at the start of the run: split 0, pos 0 = all of it goes right
+        c.split[j - 1] = G;       // default: the whole run goes left
         for (int r = 0; r < G && c.split[j - 1] == G; ++r) {
             const ShardSample &sm = by_shard[r];
             for (size_t i = 0; i < sm.key.size(); ++i) {
@@ -714,6 +715,35 @@ int b200sort_mgpu_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, i
 int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n, uint32_t *h_keys_out,
                              uint32_t *h_vals_out, int nBits, int blockSize, const int *devices, int num_devices) {
     return guarded(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, nBits, blockSize, devices, num_devices, true);
+}
+
+int b200sort_plan_owners(const uint64_t *hist, int bins, int num_shards, int *owner) {
+    if (!hist || !owner || bins < 1 || num_shards < 1) return set_error(B200SORT_EINVAL, "plan_owners arguments");
+    choose_owner(hist, bins, num_shards, owner);
+    return 0;
+}
+
+int b200sort_plan_value_cuts(const uint32_t *sample_keys, const uint64_t *sample_pos, const uint64_t *shard_offsets,
+                             int num_shards, uint64_t *values, int *split_shard, uint64_t *split_pos) {
+    if (num_shards < 1 || !shard_offsets || !values || !split_shard || !split_pos)
+        return set_error(B200SORT_EINVAL, "plan_value_cuts arguments");
+    const uint64_t total = shard_offsets[num_shards];
+    if (total && (!sample_keys || !sample_pos)) return set_error(B200SORT_EINVAL, "plan_value_cuts arguments");
+    std::vector<ShardSample> by_shard(num_shards);
+    std::vector<uint32_t> pool(sample_keys, sample_keys + total);
+    for (int r = 0; r < num_shards; ++r) {
+        if (shard_offsets[r + 1] < shard_offsets[r]) return set_error(B200SORT_EINVAL, "shard_offsets");
+        by_shard[r].key.assign(sample_keys + shard_offsets[r], sample_keys + shard_offsets[r + 1]);
+        by_shard[r].at.assign(sample_pos + shard_offsets[r], sample_pos + shard_offsets[r + 1]);
+    }
+    std::sort(pool.begin(), pool.end());
+    const ValueCuts c = value_splitters(pool, by_shard, num_shards);
+    for (int j = 0; j + 1 < num_shards; ++j) {
+        values[j] = c.value[j];
+        split_shard[j] = c.split[j];
+        split_pos[j] = c.pos[j];
+    }
+    return 0;
 }
 
 int b200sort_mgpu_last_stats(double *out, int capacity) {

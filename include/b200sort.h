@@ -98,6 +98,21 @@ int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_i
  * the splitters were key values from a sample (skewed keys; see b200sort_route) instead of bin
  * edges of the partition byte.
  * Returns the number of values written (<= capacity). */
+/* Host-side planning of the multi-GPU sorts, exported so that it can be exercised without a
+ * GPU (tests compare it with the Python driver's planner, cuda/radixsort_b200/mgpu.py).
+ * plan_owners: owner[b] = shard that receives bin b of the partition digit; cut j sits on the
+ *   bin edge closest to j * total / num_shards, owners are non-decreasing in b.
+ * plan_value_cuts: value splitters from a sample (see b200sort_route).  sample_keys/sample_pos
+ *   hold the sampled keys of all shards, shard after shard (shard r = entries shard_offsets[r]
+ *   .. shard_offsets[r+1]), with the local index each was taken from (ascending per shard).
+ *   Writes num_shards-1 cuts: the key value, the shard whose run of that value is cut, and the
+ *   local index in that shard from which equal keys go right (lower shards: left, higher: right;
+ *   split_shard == num_shards: the whole run goes left). */
+int b200sort_plan_owners(const uint64_t *hist, int bins, int num_shards, int *owner);
+int b200sort_plan_value_cuts(const uint32_t *sample_keys, const uint64_t *sample_pos,
+                             const uint64_t *shard_offsets, int num_shards, uint64_t *values,
+                             int *split_shard, uint64_t *split_pos);
+
 enum { B200SORT_MGPU_STATS = 12 };
 int b200sort_mgpu_last_stats(double *out, int capacity);
 int b200sort_mgpu_shutdown(void);

@@ -286,3 +286,54 @@ def test_sample_indices():
     assert mgpu.sample_indices(0).size == 0
     v, r, c = mgpu.value_splitters(np.zeros(0, np.uint32), [np.zeros(0, np.uint32)] * 4, [np.zeros(0, np.int64)] * 4, 4)
     assert v.shape == (3,) and r.shape == (3,) and c.shape == (3,)
+
+
+def test_c_planners_agree_with_the_python_driver(rs):
+    """The single-process driver (csrc/mgpu_host.cu) and the torch.distributed driver (mgpu.py) plan
+    with separate implementations of the same rules; both are exported/pure, so compare them here."""
+    import ctypes as C
+    lib = rs.load()
+    rng = np.random.default_rng(31)
+    for trial in range(40):
+        world = int(rng.choice([2, 4, 8, 16]))
+        hist = rng.integers(0, 1000, 256).astype(np.uint64)
+        if trial % 3 == 0:
+            hist[rng.integers(0, 256)] += np.uint64(rng.integers(10 ** 4, 10 ** 6))    # a heavy bin
+        if trial % 7 == 0:
+            hist[:] = 0
+            hist[rng.integers(0, 256)] = 12345                                           # a single bin
+        owner = np.zeros(256, dtype=np.int32)
+        assert lib.b200sort_plan_owners(hist.ctypes.data, 256, world, owner.ctypes.data) == 0
+        assert np.array_equal(owner, mgpu.choose_owner(hist.astype(np.int64), world)), (trial, world)
+    for trial in range(40):
+        world = int(rng.choice([2, 3, 4, 8]))
+        m = int(rng.choice([64, 257, 1024]))
+        sizes = [int(rng.integers(m, 50 * m)) for _ in range(world)]
+        if trial % 5 == 0:
+            sizes[int(rng.integers(0, world))] = 0                                       # an empty shard
+        kind = trial % 4
+        samples, positions = [], []
+        for n_local in sizes:
+            pos = mgpu.sample_indices(n_local, m)
+            if kind == 0:
+                keys = rng.integers(0, 1 << 32, pos.size, dtype=np.uint64)
+            elif kind == 1:
+                keys = rng.integers(0, 5, pos.size, dtype=np.uint64) * 1000                # few values
+            elif kind == 2:
+                keys = np.where(rng.random(pos.size) < 0.7, 0xFFFFFFFF, rng.integers(0, 1 << 32, pos.size, dtype=np.uint64))
+            else:
+                keys = np.full(pos.size, 42, dtype=np.uint64)                               # all equal
+            samples.append(keys.astype(np.uint32))
+            positions.append(pos.astype(np.uint64))
+        pool = np.sort(np.concatenate(samples))
+        want_v, want_r, want_p = mgpu.value_splitters(pool, samples, positions, world)
+        cat_k = np.ascontiguousarray(np.concatenate(samples))
+        cat_p = np.ascontiguousarray(np.concatenate(positions))
+        offs = np.concatenate([[0], np.cumsum([s.size for s in samples])]).astype(np.uint64)
+        v = np.zeros(world - 1, np.uint64); r = np.zeros(world - 1, np.int32); p = np.zeros(world - 1, np.uint64)
+        assert lib.b200sort_plan_value_cuts(cat_k.ctypes.data, cat_p.ctypes.data, offs.ctypes.data, world,
+                                            v.ctypes.data, r.ctypes.data, p.ctypes.data) == 0
+        assert np.array_equal(v.astype(np.int64), want_v), (trial, kind, world)
+        assert np.array_equal(r.astype(np.int64), want_r), (trial, kind, world)
+        assert np.array_equal(p.astype(np.int64), want_p), (trial, kind, world)
+    assert lib.b200sort_plan_owners(None, 256, 2, None) == -1
