@@ -17,6 +17,12 @@ The reference has nothing multi-GPU; the parity target is
 Receive offsets are ordered by source rank and every step is stable, so equal keys keep their
 global input order (matters for the key/value variant).
 
+Skewed keys (bin edges would leave a shard above balance_threshold x the mean): the splitters
+become cuts of the key space taken from a sample -- value_splitters() below -- and the
+partition runs on a route array (b200sort_route: destination of every key) that carries the
+real keys; see ShardedSorter._sort_by_value_splitters.  The single-process twin of this driver
+is csrc/mgpu_host.cu (b200sort_mgpu_*_host); tests compare the two planners.
+
 `ops` abstracts the device kernels so that the orchestration (everything in this file) can be
 exercised on CPU with the gloo backend in tests (tests/test_mgpu_cpu.py supplies numpy ops);
 the product always uses DeviceOps.
