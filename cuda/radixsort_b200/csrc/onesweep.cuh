@@ -23,7 +23,7 @@
 //                shared-memory ADDRESS of the first key of (warp w, bin d)
 //   4. rank      address of every key in stable order (three interchangeable modes, below);
 //                the key is stored there, so each bin's keys end up contiguous
-//   5. look-back thread d walks the predecessors' descriptors of bin d, four at a time, then
+//   5. look-back thread d walks the predecessors' descriptors of bin d, LB at a time (8), then
 //                publishes the INCLUSIVE descriptor.  Placed after (4) so that predecessors
 //                have had the whole rank phase to publish.
 //   6. write     thread t copies tile positions t, t+THREADS, ...: inside a bin run consecutive
@@ -35,14 +35,14 @@
 //                digit's high TB bits (32 entries -> bank-conflict free) AND'ed with ballots on
 //                the remaining low bits; the highest peer fetches the run's base with ONE
 //                shared atomicAdd(count) (distinct addresses -> fully defined) and broadcasts it.
-//   RANK_ATOMIC  address = atomicAdd(&s_cnt[warp][digit], 4) by every lane.  Needs same-address
-//                shared atomics of one warp instruction to be applied in ascending lane order;
-//                PTX does not promise that, so the host only selects this mode after the
-//                on-device self test (atomic_order_selftest) passes.
 //                With TB = 0 the table disappears and the ballots alone find the peers: the mode
 //                used for digits of <= 3 bits (2..8 bins), where almost every lane has peers
 //                and same-address atomics with a return value would serialise (measured: 18
 //                cycles per warp instruction at 2 distinct addresses, 32 at one).
+//   RANK_ATOMIC  address = atomicAdd(&s_cnt[warp][digit], 4) by every lane.  Needs same-address
+//                shared atomics of one warp instruction to be applied in ascending lane order;
+//                PTX does not promise that, so the host only selects this mode after the
+//                on-device self test (atomic_order_selftest) passes.
 //   RANK_MATCH   match.any.sync peers (the textbook form).  Kept for the record: MATCH.ANY
 //                issues at ~1 warp instruction / 61 cycles / SM on B200, 2.4 ms per pass.
 //
