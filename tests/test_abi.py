@@ -129,3 +129,19 @@ def test_product_does_not_import_the_oracle():
         src = open(os.path.join(pkg, "csrc", name)).read()
         code = re.sub(r"//.*", "", re.sub(r"/\*.*?\*/", "", src, flags=re.S))   # comments may cite it
         assert "oracle" not in code, name
+
+
+def test_headers_compile_as_plain_c_and_cxx():
+    """include/b200sort.h is a C header (the boundary a C, Go/cgo or JNI host would bind);
+    include/radix_sort_compat.hpp is the C++ shim with the reference's spellings."""
+    import shutil
+    import subprocess
+    inc = os.path.dirname(HEADER)
+    if shutil.which("gcc"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    if shutil.which("g++"):
+        r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++",
+                            os.path.join(inc, "radix_sort_compat.hpp")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
