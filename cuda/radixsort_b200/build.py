@@ -25,6 +25,10 @@ INCLUDE_DIR = os.path.normpath(os.path.join(PKG_DIR, "..", "..", "include"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-I", INCLUDE_DIR]
+if os.environ.get("B200_COL_NOTMA"):
+    NVCC_FLAGS.append("-DB200_COL_NOTMA")  # experiment: tile loaded with LDG + STS instead of the bulk-copy engine
+if os.environ.get("B200_COL_DEBUG"):
+    NVCC_FLAGS.append("-DB200_COL_DEBUG")  # per-phase clock stamps in the column-sweep kernel (tools/col_timeline.py)
 WIDTHS = range(1, 9)
 
 

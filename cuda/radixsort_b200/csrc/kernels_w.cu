@@ -6,6 +6,7 @@
 #include "hist.cuh"
 #include "launch.h"
 #include "onesweep.cuh"
+#include "colsweep.cuh"
 
 #ifndef B200_W
 #error "compile with -DB200_W=<1..8>"
@@ -18,7 +19,28 @@ constexpr int W = B200_W;
 constexpr int P_UNIFORM = (32 + W - 1) / W;
 
 template <int V, bool PAIRS, bool DST>
-cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
+cudaError_t launch_col_variant(const PassArgs &a, cudaStream_t s) {
+    constexpr PassVariant g = kVariants[V];
+    constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
+    constexpr int WARPS = g.threads / 32;
+    constexpr int GROUP = g.table_bits < ITEMS ? g.table_bits : ITEMS;
+    using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST>;
+    auto kernel = colsweep_pass_kernel<W, WARPS, ITEMS, g.min_ctas, g.lb_batch, GROUP, PAIRS, DST>;
+    static std::atomic<uint64_t> configured{0};  // one bit per device: the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured.load(std::memory_order_acquire) >> (dev & 63) & 1u)) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TR::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    kernel<<<a.num_tiles, g.threads, TR::SMEM_BYTES, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int V, bool PAIRS, bool DST>
+cudaError_t launch_one_variant(const PassArgs &a, cudaStream_t s) {
     constexpr PassVariant g = kVariants[V];
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
     constexpr int TB = g.table_bits;
@@ -51,11 +73,17 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+template <int V, bool PAIRS, bool DST>
+cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
+    if constexpr (kVariants[V].mode == 3) return launch_col_variant<V, PAIRS, DST>(a, s);
+    else return launch_one_variant<V, PAIRS, DST>(a, s);
+}
+
 template <int V>
 cudaError_t launch_modes(bool pairs, bool dst, const PassArgs &a, cudaStream_t s) {
     if (!pairs && !dst) return launch_variant<V, false, false>(a, s);
     if (pairs && !dst) return launch_variant<V, true, false>(a, s);
-    if constexpr (V <= 1 || V == kBallotVariant || V == kBallotSmallVariant) {
+    if constexpr (V <= 1 || V == kBallotVariant || V == kBallotSmallVariant || V == kColVariant) {
         if (!pairs && dst) return launch_variant<V, false, true>(a, s);
         return launch_variant<V, true, true>(a, s);
     }
@@ -90,7 +118,7 @@ cudaError_t B200_CAT(launch_hist_w, B200_W)(bool uniform, const HistArgs &a, int
 
 cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, const PassArgs &a,
                                             cudaStream_t s) {
-    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant) variant = 0;
+    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant && variant != kColVariant) variant = 0;
     switch (variant) {
     case 0: return launch_modes<0>(pairs, dst, a, s);
     case 1: return launch_modes<1>(pairs, dst, a, s);
@@ -129,10 +157,24 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 33: return launch_modes<33>(pairs, dst, a, s);
     case 34: return launch_modes<34>(pairs, dst, a, s);
     case 35: return launch_modes<35>(pairs, dst, a, s);
+    case 36: return launch_modes<36>(pairs, dst, a, s);
+    case 37: return launch_modes<37>(pairs, dst, a, s);
+    case 38: return launch_modes<38>(pairs, dst, a, s);
+    case 39: return launch_modes<39>(pairs, dst, a, s);
+    case 40: return launch_modes<40>(pairs, dst, a, s);
+    case 41: return launch_modes<41>(pairs, dst, a, s);
+    case 42: return launch_modes<42>(pairs, dst, a, s);
+    case 43: return launch_modes<43>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }
 }
+
+#if B200_W == 8 && defined(B200_COL_DEBUG)
+extern "C" int b200sort_debug_read(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, g_col_dbg, sizeof(long long) * 16 * 20);
+}
+#endif
 
 #if B200_W == 8
 cudaError_t run_atomic_order_selftest(uint32_t *d_counter, int blocks, int rounds, cudaStream_t s) {

@@ -13,12 +13,12 @@ struct PassVariant {
     int items_keys;
     int items_pairs;
     int min_ctas;
-    int mode;
-    int table_bits;
+    int mode;        // 0 table rank, 1 atomic rank, 2 match.any (onesweep.cuh); 3 = column sweep (colsweep.cuh)
+    int table_bits;  // mode 0: bits of the peer table; mode 3: ranking atomics in flight per thread
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA
 };
-constexpr int kNumVariants = 36;
+constexpr int kNumVariants = 44;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -56,12 +56,22 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 36, 20, 4, 1, 0, 8, 2},   // 33 TMA, four CTAs per SM
     {256, 64, 44, 2, 1, 0, 8, 0},   // 34 two CTAs per SM: 64 keys or 44 pairs per thread
     {256, 64, 36, 2, 1, 0, 8, 0},   // 35
+    // column sweep (colsweep.cuh): threads = 32 x (odd warp count), keys per thread % 8 == 4
+    {288, 36, 20, 3, 3, 12, 8, 0},  // 36 nine warps x 36 keys, three CTAs per SM, 12 ranking atomics in flight, 8-deep look-back
+    {288, 36, 20, 3, 3, 12, 4, 0},  // 37 = 36, 4-deep look-back
+    {288, 36, 20, 3, 3, 12, 12, 0}, // 38 = 36, 12-deep look-back
+    {288, 36, 20, 2, 3, 36, 8, 0},  // 39 two CTAs per SM, a whole turn in flight
+    {288, 52, 28, 2, 3, 26, 8, 0},  // 40
+    {288, 28, 20, 3, 3, 28, 8, 0},  // 41 28 keys, a whole turn in flight
+    {288, 36, 20, 3, 3, 36, 8, 0},  // 42 = 36, a whole turn in flight
+    {288, 28, 12, 4, 3, 14, 8, 0},  // 43 four CTAs per SM
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
     return g.threads * (pairs ? g.items_pairs : g.items_keys);
 }
 inline int variant_mode(int variant) { return kVariants[variant].mode; }
+constexpr int kColVariant = 36;  // column-sweep default geometry
 // Smallest tile over all variants: bounds the descriptor array when sizing temp storage.
 constexpr int kMinTileKeys = 2048;
 

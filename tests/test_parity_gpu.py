@@ -204,7 +204,7 @@ def test_multi_launch_portions(rs, oracle):
         rs.set_param("portion_tiles", 0)
 
 
-@pytest.mark.parametrize("variant", list(range(36)))
+@pytest.mark.parametrize("variant", list(range(44)))
 def test_kernel_variants(rs, oracle, variant):
     rs.set_param("variant", variant)
     try:
