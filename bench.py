@@ -59,6 +59,40 @@ def committed_traffic(kernel: str):
         return None
 
 
+def committed_traffic_source():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("_source")
+    except Exception:
+        return None
+
+
+def _run_json(cmd, timeout):
+    """Runs a helper process and returns the last JSON line it printed (or an 'unavailable' note)."""
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"unavailable": f"rc={r.returncode}: {(r.stderr or r.stdout)[-200:]}"}
+    except Exception as e:  # missing binary, timeout
+        return {"unavailable": repr(e)[:200]}
+
+
+def same_box_gpu_baselines(log2n: int, nbits: int):
+    """The two GPU bars BASELINE.md promises beside our number, timed in this run on this GPU, each in
+    its own process: (1) the reference's best version as shipped -- Parallel7 sortByDevice, unmodified
+    (oracle/_ref; Parallel7.cu:530-639), host arrays in and out; (2) device-resident
+    cub::DeviceRadixSort, what the reference's sortByThrust (Baseline1.cu:66-70) resolves to
+    (tools/cub_bench.cu, a bench-only binary: libb200sort.so links neither CUB nor Thrust)."""
+    ref = _run_json([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_time.py"), "--log2n", str(log2n),
+                     "--nbits", str(nbits), "--block", "512"], timeout=300)
+    cub_bin = os.path.join(ROOT, "tools", "_bin", "cub_bench")
+    cub = _run_json([cub_bin, str(log2n), "10"], timeout=300) if os.path.exists(cub_bin) else \
+        {"unavailable": "tools/_bin/cub_bench not built (__graft_entry__.build())"}
+    return ref, cub
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -137,7 +171,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # One core sorts ~45 Mkeys/s: the full 2^28-key workload takes ~6 s per step.  Sort the REAL n when
+    # the whole run stays within a few minutes, else a bounded sample (and say which: `sample_n`).
     sample_log2 = args.cpu_sample_log2
+    if args.gpus == 1 and (args.steps + args.warmup) * (1 << args.log2n) * 22e-9 <= 240.0:
+        sample_log2 = args.log2n
     times = []
     import oracle as O
     n = 1 << sample_log2
@@ -153,8 +191,12 @@ def run_reference_arm(args):
     assert O.is_sorted(out)
     total = sum(times)
     value = n * args.steps / total
-    sample = (f"2^{sample_log2} uniform uint32 keys per step (bounded sample of the 2^{args.log2n}-key "
-              f"workload), sortByHost nBits={args.nbits}, single thread")
+    workload_log2 = args.log2n if args.gpus == 1 else args.log2n_multi
+    sample = (f"2^{sample_log2} uniform uint32 keys per step ("
+              + ("the full workload" if sample_log2 == workload_log2 else
+                 f"a bounded sample of the 2^{workload_log2}-key workload: keys/s of a counting sort does not "
+                 f"grow with n, and sortByHost takes an int n")
+              + f"), sortByHost nBits={args.nbits}, single thread")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -165,6 +207,7 @@ def run_reference_arm(args):
                          "kind": "reference" if use_ref else "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "sample_n": n, "workload_n": 1 << workload_log2,
         "host": {"nproc": os.cpu_count()},
     }
     print(json.dumps(line), flush=True)
@@ -198,6 +241,9 @@ def run_single(args):
     rs.load()
     n = 1 << args.log2n
     nbits = args.nbits
+    gpu_reference = cub = None
+    if not args.no_gpu_baselines:
+        gpu_reference, cub = same_box_gpu_baselines(args.log2n, nbits)
     pairs = args.workload == "pairs"
     dist = "uniform" if pairs else args.workload
     cdf = None
@@ -254,11 +300,13 @@ def run_single(args):
     bytes_per_key = 16 if pairs else 8
     pass_avg = sum(pass_ms) / max(1, len(pass_ms))
     achieved = bytes_per_key * n / (pass_avg * 1e-3) / 1e9 if pass_ms else None
+    eff_variant = rs.get_param("effective_variant") if not pairs else None
     kernel_name = "onesweep_pass_kernel"
     roofline = {
         "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": (achieved / peak) if achieved else None,
         "traffic": committed_traffic(kernel_name),
+        "traffic_source": "NOT measured in this run: " + str(committed_traffic_source()),
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": bytes_per_key * n,
         "avg_launch_ms": pass_avg, "launches_timed": len(pass_ms),
@@ -291,12 +339,34 @@ def run_single(args):
         for _ in range(e2e_steps):
             call()
         dt = (time.perf_counter() - t0) / e2e_steps
-        assert a_out[0] <= a_out[n // 2] <= a_out[-1]
+        # the host-path output is checked like the device-resident one: inversions + multiset fingerprint
+        chk = torch.empty_like(keys)
+        chk.copy_(h_out)
+        bad_e, s_e, h_e, x_e = rs.verify(chk)
+        assert bad_e == 0 and (s_e, h_e, x_e) == (s0, h0, x0), "e2e output is not a sorted permutation of the input"
+        if pairs:
+            chk.copy_(hv_out)
+            assert torch.equal(keys[chk.to(torch.int64) & 0xFFFFFFFF], out), "e2e values do not follow their keys"
+        del chk
         per = 8 * n if pairs else 4 * n
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": per, "d2h_bytes_per_step": per,
-               "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "ms_per_step": dt * 1e3, "steps": e2e_steps, "verified": True,
                "how": "blocking host-pointer call sort(in,n,out,SORT_BY_DEVICE,nBits,512) on pinned "
                       "host buffers; wall clock around the calls (H2D + sort + D2H inside)"}
+        if not pairs:
+            # the reference's own caller passes malloc'ed (pageable) arrays (Parallel7.cu:712-715): same call
+            p_in = np.array(a_in, copy=True)
+            p_out = np.empty_like(p_in)
+            rs.sort(p_in, n, p_out, rs.SORT_BY_DEVICE, nbits, 512)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                rs.sort(p_in, n, p_out, rs.SORT_BY_DEVICE, nbits, 512)
+            dtp = (time.perf_counter() - t0) / 2
+            assert np.array_equal(p_out[:: 1 << 12], a_out[:: 1 << 12])
+            e2e["pageable"] = {"value": n / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": 2,
+                               "how": "same call on pageable (numpy-owned) host arrays, staged through the "
+                                      "library's pinned ring by its host copy threads"}
+            del p_in, p_out
         del h_in, h_out
 
     # ---- CPU baseline (reported, not the target) ---------------------------------------------
@@ -315,9 +385,59 @@ def run_single(args):
         "config": workload_config(args, 1),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "variant": rs.get_param("variant"), "tile_keys": rs.tile_keys(pairs),
+        "effective_variant": eff_variant, "atomic_rank_ok": rs.get_param("atomic_rank_ok"),
+        "gpu_reference": gpu_reference, "cub": cub,
+        "parity_note": ("pairs: parity unpinned by the reference (it has no key/value path); checked against the "
+                        "payload-carrying restatement of Baseline1's counting sort") if pairs else None,
     }
+    if gpu_reference and "ms" in gpu_reference and e2e:
+        line["vs_gpu_reference_e2e"] = gpu_reference["ms"] / e2e["ms_per_step"]
+    if cub and "sortkeys_ms" in cub:
+        line["vs_cub_device_resident"] = (cub["sortpairs_ms"] if pairs else cub["sortkeys_ms"]) / ms_per_step
     print(json.dumps(line), flush=True)
     return 0
+
+
+def bit_exact_sharded_check(rs, mgpu, dist, args, rank, world, log2n=24):
+    """The sharded sort against the oracle (checker only) at a size the CPU sort finishes in a second:
+    concatenated shards == sortByHost of the whole input (Baseline1.cu:15-64)."""
+    import torch
+    total = (1 << log2n) + 4321
+    per = total // world
+    first = rank * per
+    count = per if rank < world - 1 else total - first
+    ok_all = True
+    for kind in ("uniform", "zipf"):
+        cdf = None
+        if kind == "zipf":
+            import oracle as O
+            cdf = O.zipf_cdf()
+        keys = rs.generate(kind, count, first=first, total=total, zipf_cdf=cdf)
+        sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=total + 1024, nbits=args.nbits,
+                                    fused=not args.no_fused, allow_narrow=not args.no_narrow,
+                                    balance_threshold=args.balance_threshold)
+        res = sorter.sort(keys)
+        sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+        sizes[rank] = res.numel()
+        dist.all_reduce(sizes)
+        off = int(sizes[:rank].sum().item())
+        whole_out = torch.zeros(total, dtype=torch.int32, device="cuda")
+        whole_out[off:off + res.numel()] = res
+        dist.all_reduce(whole_out)                       # disjoint slices: sum == concatenation
+        whole_in = torch.zeros(total, dtype=torch.int32, device="cuda")
+        whole_in[first:first + count] = keys
+        dist.all_reduce(whole_in)
+        ok = torch.ones(1, device="cuda", dtype=torch.int32)
+        if rank == 0:
+            import oracle as O
+            exp = O.sort_keys(whole_in.cpu().numpy().view(np.uint32), args.nbits)
+            if not np.array_equal(whole_out.cpu().numpy().view(np.uint32), exp):
+                ok.zero_()
+        dist.broadcast(ok, 0)
+        ok_all = ok_all and bool(ok.item())
+        del sorter, res, whole_in, whole_out
+    torch.cuda.empty_cache()
+    return ok_all
 
 
 def run_multi(args):
@@ -343,6 +463,9 @@ def run_multi(args):
     keys = rs.generate(kind, per, first=rank * per, total=total, zipf_cdf=cdf)
     vals = torch.arange(rank * per, (rank + 1) * per, dtype=torch.int64, device="cuda").to(torch.int32) if pairs else None
     slack = 1.02 if kind == "uniform" else 1.6      # skewed keys: value splitters never split one value
+    bit_exact = None
+    if not args.no_bit_exact:
+        bit_exact = bit_exact_sharded_check(rs, mgpu, dist, args, rank, world)
     sorter = mgpu.ShardedSorter(dist.group.WORLD, per_rank_capacity=int(per * slack) + (1 << 20),
                                 nbits=args.nbits, fused=not args.no_fused, allow_narrow=not args.no_narrow,
                                 balance_threshold=args.balance_threshold)
@@ -385,11 +508,14 @@ def run_multi(args):
         if int(flag.item()) == 1:
             d_in = torch.empty_like(keys)
 
+            last = {}
+
             def e2e_step():
                 d_in.copy_(h_in, non_blocking=True)
                 res = sorter.sort(d_in)
                 h_out[: res.numel()].copy_(res, non_blocking=True)
                 torch.cuda.synchronize()
+                last["res"] = res
                 return res.numel()
 
             e2e_step()
@@ -403,9 +529,14 @@ def run_multi(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             moved = torch.tensor([per * 4, got * 4], device="cuda", dtype=torch.int64)
             dist.all_reduce(moved)
+            # what came back to the host is the rank's sorted slice: re-upload it and run the sharded checks
+            back = torch.empty(got, dtype=torch.int32, device="cuda")
+            back.copy_(h_out[:got])
+            e2e_ok = bool(mgpu.verify_sharded(back, keys, dist.group.WORLD))
+            del back
             e2e = {"value": total / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(moved[0].item()),
                    "d2h_bytes_per_step": int(moved[1].item()), "ms_per_step": float(dt.item()) * 1e3,
-                   "steps": e2e_steps,
+                   "steps": e2e_steps, "verified": e2e_ok,
                    "how": "per rank: pinned host shard -> H2D -> ShardedSorter.sort -> D2H of the rank's sorted "
                           "slice into pinned host memory; wall clock, max over ranks"}
     if rank == 0:
@@ -415,7 +546,10 @@ def run_multi(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": workload_config(args, world),
-            "phases_ms": phases, "verified": bool(ok), "gpu_launches": int(launches.item()),
+            "phases_ms": phases, "verified": bool(ok), "bit_exact": bit_exact,
+            "bit_exact_how": "before the timed region: the same ShardedSorter on 2^24+4321 uniform and Zipf keys, "
+                             "concatenated shards compared with the oracle's sortByHost restatement on rank 0",
+            "gpu_launches": int(launches.item()),
             "clocks": clocks, "roofline": None, "cpu_baseline": None, "e2e": e2e,
         }
         print(json.dumps(line), flush=True)
@@ -441,6 +575,9 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpu-baselines", action="store_true",
+                    help="skip the same-box Parallel7 sortByDevice and cub::DeviceRadixSort timings")
+    ap.add_argument("--no-bit-exact", action="store_true", help="multi-GPU: skip the 2^24-key oracle comparison")
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-narrow", action="store_true")
     ap.add_argument("--narrow-variant", type=int, default=None)
