@@ -28,19 +28,32 @@ namespace {
 thread_local std::string g_last_error = "";
 std::atomic<uint64_t> g_launches{0};
 
+// Tuning parameters: process-wide, read once per call into locals (b200sort_set_param is meant for
+// benches and tests; changing a parameter while another thread is inside a sort affects only later calls).
 struct Params {
-    int variant = -1;  // -1 = automatic choice (see effective_variant)
-    int portion_tiles = 0;  // 0 = as many as fit the 30-bit descriptor value
-    int hist_ctas_per_sm = 2;
-    int narrow_variant = -1;  // digit passes of <= 3 bits: -1 = kBallotVariant
+    std::atomic<int> variant{-1};        // -1 = automatic choice (see effective_variant)
+    std::atomic<int> portion_tiles{0};   // 0 = as many as fit the 30-bit descriptor value
+    std::atomic<int> hist_ctas_per_sm{2};
+    std::atomic<int> narrow_variant{-1}; // digit passes of <= 3 bits: -1 = kBallotVariant
+    std::atomic<int> safe_rank{0};       // 1 = only kernels whose ranking follows from the PTX memory model
 } g_params;
 
-// RANK_ATOMIC variants are only used after the on-device self test has passed.
-// -1 = not run yet, 0 = failed (fall back to the table-rank twin), 1 = passed.
-std::atomic<int> g_atomic_rank_ok{-1};
+// Per CUDA ordinal: the sm_100 check, the SM count and the verdict of the RANK_ATOMIC self test
+// (-1 = not run yet, 0 = failed -> spec-safe column-sweep kernel, 1 = passed).
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    std::atomic<int> checked{-1000};
+    std::atomic<int> sms{0};
+    std::atomic<int> atomic_rank_ok{-1};
+};
+DeviceState g_dev[kMaxDevices];
 
-std::atomic<int> g_num_sms{0};
-std::atomic<int> g_device_checked{-1000};
+DeviceState &dev_state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return g_dev[dev & (kMaxDevices - 1)];
+}
+int num_sms() { return dev_state().sms.load(); }
 
 int fail(int code, const char *what) {
     g_last_error = std::string(what) + ": " + b200sort_error_string(code);
@@ -57,7 +70,8 @@ int fail_cuda(cudaError_t e, const char *what) {
     } while (0)
 
 int check_device() {
-    if (g_device_checked != -1000) return g_device_checked;
+    DeviceState &st = dev_state();
+    if (st.checked != -1000) return st.checked;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) {
@@ -73,8 +87,8 @@ int check_device() {
                        std::to_string(minor);
         return B200SORT_ENODEVICE;
     }
-    g_num_sms = sms;
-    g_device_checked = 0;
+    st.sms = sms;
+    st.checked = 0;
     return 0;
 }
 
@@ -155,19 +169,23 @@ Layout make_layout(uint64_t n, int passes, int width, bool pairs, bool need_alt,
 
 int check_device();
 
+// The self test of the current device (once per device and process): three CTAs per SM, half of the
+// warps replay random digit patterns with per-lane addends against the ranking atomics while the other
+// half hammers the same banks with stores, loads and reductions (see atomic_order_selftest).
 int run_selftest() {
-    if (g_atomic_rank_ok >= 0) return g_atomic_rank_ok;
+    DeviceState &st = dev_state();
+    if (st.atomic_rank_ok >= 0) return st.atomic_rank_ok;
     if (check_device() != 0) return 0;  // not cached: no device yet
     uint32_t *d_counter = nullptr;
     uint32_t h = 1;
-    if (cudaMalloc(&d_counter, sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return 0; }
-    bool ok = cudaMemset(d_counter, 0, sizeof(uint32_t)) == cudaSuccess &&
-              run_atomic_order_selftest(d_counter, g_num_sms * 2, 4096, nullptr) == cudaSuccess &&
+    if (cudaMalloc(&d_counter, 2 * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    bool ok = cudaMemset(d_counter, 0, 2 * sizeof(uint32_t)) == cudaSuccess &&
+              run_atomic_order_selftest(d_counter, st.sms * 3, 2048, nullptr) == cudaSuccess &&
               cudaMemcpy(&h, d_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaFree(d_counter);
-    g_atomic_rank_ok = (ok && h == 0) ? 1 : 0;
-    return g_atomic_rank_ok;
+    st.atomic_rank_ok = (ok && h == 0) ? 1 : 0;
+    return st.atomic_rank_ok;
 }
 
 // Automatic choice: the fastest measured geometry (profiles/r01_sweep_*.jsonl) in atomic-rank mode
@@ -177,15 +195,16 @@ constexpr int kAutoVariantW8Pairs = 35;  // pairs: 256 threads x 36 pairs, two C
 
 int effective_variant(int width, bool pairs = false) {
     int v = g_params.variant;
+    const int narrow = g_params.narrow_variant;
     if (v < 0)
         v = (width == 8) ? (pairs ? kAutoVariantW8Pairs : kAutoVariantW8)
-                         : (width <= 3 ? (g_params.narrow_variant >= 0 ? g_params.narrow_variant : kBallotVariant) : 1);
+                         : (width <= 3 ? (narrow >= 0 ? narrow : kBallotVariant) : 1);
     if (!variant_available(width, v)) v = 0;
-    if (variant_mode(v) == 1 && !run_selftest()) {
-        // same geometry, table rank: variants are laid out as (table, atomic) twins where possible
-        v = (v >= 1 && variant_mode(v - 1) == 0 && kVariants[v - 1].threads == kVariants[v].threads &&
-             kVariants[v - 1].items_keys == kVariants[v].items_keys) ? v - 1 : 0;
-    }
+    // Atomic-rank kernels need same-address shared atomics of one warp instruction to be applied in lane
+    // order (not promised by PTX): they run only on a device that passed the self test, and never when
+    // the caller asked for spec-safe ranking -- the column-sweep kernel (lane-private counters, ordered
+    // by named barriers) takes over; ballot-only variants (mode 0, no table) are spec-safe as they are.
+    if (variant_mode(v) == 1 && (g_params.safe_rank || !run_selftest())) v = kColVariant;
     return v;
 }
 
@@ -196,7 +215,7 @@ size_t temp_upper_bound(uint64_t n, int nbits, bool pairs) {
     if (!build_pass_list(nbits, pl)) return 0;
     Layout L = make_layout(n, pl.count, pl.width, pairs, true, kMinTileKeys, 0);
     size_t tickets = 0;  // a forced small portion size (tests) multiplies the launches per pass
-    if (g_params.portion_tiles > 0)
+    if (g_params.portion_tiles.load() > 0)
         tickets = (size_t)pl.count * (((n + kMinTileKeys - 1) / kMinTileKeys) / g_params.portion_tiles + 2) * 4;
     return L.total + align_up(tickets, 256) + 4096;
 }
@@ -259,7 +278,7 @@ int hist_grid(uint64_t n, int passes, int width) {
     const size_t smem = hist_smem_bytes(passes, width) + 1024;
     int ctas = (int)std::min<size_t>((size_t)g_params.hist_ctas_per_sm, (227u * 1024u) / smem);
     ctas = std::max(1, std::min(ctas, 2048 / kHistThreads));
-    return (int)std::min<uint64_t>(want, (uint64_t)g_num_sms * ctas);
+    return (int)std::min<uint64_t>(want, (uint64_t)num_sms() * ctas);
 }
 
 bool ranges_overlap(const void *a, const void *b, uint64_t bytes) {
@@ -567,6 +586,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.hist_ctas_per_sm = value;
         return 0;
     }
+    if (!strcmp(name, "safe_rank")) {
+        if (value != 0 && value != 1) return B200SORT_EINVAL;
+        g_params.safe_rank = value;
+        return 0;
+    }
     return B200SORT_EINVAL;
 }
 
@@ -577,7 +601,9 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
     if (!strcmp(name, "mgpu_balance_permille")) return g_mgpu_balance_permille.load();
     if (!strcmp(name, "num_variants")) return kNumVariants;
-    if (!strcmp(name, "effective_variant")) return check_device() ? std::max(g_params.variant, 0) : effective_variant(8);
+    if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
+    if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
+    if (!strcmp(name, "effective_variant")) return check_device() ? std::max<int>(g_params.variant.load(), 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
     return B200SORT_EINVAL;
 }
@@ -672,8 +698,9 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     cudaStream_t s = (cudaStream_t)stream;
 
     int variant = effective_variant(bits, pairs);
-    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant)
+    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant && variant != kColVariant)
         variant = variant_mode(variant) == 1 ? 1 : 0;
+    if (variant_mode(variant) == 1 && (g_params.safe_rank || !run_selftest())) variant = kColVariant;
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);
     if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage");
@@ -756,7 +783,7 @@ int b200sort_generate(uint32_t *d_out, uint64_t first, uint64_t count, int kind,
     if (!d_out) return fail(B200SORT_EINVAL, "null buffer");
     int rc = check_device();
     if (rc) return rc;
-    const int grid = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)g_num_sms * 16);
+    const int grid = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)num_sms() * 16);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     generate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_out, first, count, kind, total, d_zipf_cdf);
     CU(cudaGetLastError());
@@ -773,7 +800,7 @@ int b200sort_route(const uint32_t *d_keys, uint64_t n, const uint64_t *d_thresho
     if (d_counts) CU(cudaMemsetAsync(d_counts, 0, (size_t)(count + 1) * sizeof(uint32_t), s));
     if (n == 0) return 0;
     const uint64_t want = (n + 256ull * 8 - 1) / (256ull * 8);
-    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)g_num_sms * 8);
+    const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)num_sms() * 8);
     if (count <= kRouteRegCuts)
         route_kernel<true><<<grid, 256, 0, s>>>(d_keys, n, d_thresholds, count, d_route, d_counts);
     else
@@ -788,7 +815,7 @@ int b200sort_store_probe(uint32_t *d_dst, const uint32_t *d_src, uint64_t n, int
     int rc = check_device();
     if (rc) return rc;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    store_probe_kernel<<<g_num_sms * ctas_per_sm, 256, 0, (cudaStream_t)stream>>>(d_dst, d_src, n, vec);
+    store_probe_kernel<<<num_sms() * ctas_per_sm, 256, 0, (cudaStream_t)stream>>>(d_dst, d_src, n, vec);
     CU(cudaGetLastError());
     return 0;
 }
@@ -800,7 +827,7 @@ int b200sort_verify(const uint32_t *d_keys, uint64_t n, uint64_t *d_result, void
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(d_result, 0, 4 * sizeof(uint64_t), s));
     if (n == 0) return 0;
-    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)g_num_sms * 16);
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)num_sms() * 16);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     verify_kernel<<<grid, 256, 0, s>>>(d_keys, n, reinterpret_cast<unsigned long long *>(d_result));
     CU(cudaGetLastError());

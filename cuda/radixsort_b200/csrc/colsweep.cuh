@@ -95,7 +95,7 @@ struct ColTraits {
     static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);     // [B] x 64 bit (DST pairs)
     static constexpr int OFF_ROWTOT = OFF_VBASE + ((DST && PAIRS) ? 2 * B : 0);  // [ROWS]
     static constexpr int OFF_MISC = OFF_ROWTOT + ROWS;                  // warp totals [32] + pad
-    static constexpr int OFF_BAR = OFF_MISC + 36;                       // mbarrier (8 bytes, 8-byte aligned)
+    static constexpr int OFF_BAR = (OFF_MISC + 36 + 1) / 2 * 2;          // mbarrier (8 bytes, 8-byte aligned)
     static constexpr int SMEM_WORDS = OFF_BAR + 2;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
     static_assert(W >= 1 && W <= 8, "digit width");

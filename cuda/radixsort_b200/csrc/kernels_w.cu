@@ -124,6 +124,7 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 1: return launch_modes<1>(pairs, dst, a, s);
     case kBallotVariant: return launch_modes<kBallotVariant>(pairs, dst, a, s);
     case kBallotSmallVariant: return launch_modes<kBallotSmallVariant>(pairs, dst, a, s);
+    case kColVariant: return launch_modes<kColVariant>(pairs, dst, a, s);
 #if B200_W == 8
     case 2: return launch_modes<2>(pairs, dst, a, s);
     case 3: return launch_modes<3>(pairs, dst, a, s);
@@ -157,7 +158,6 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 33: return launch_modes<33>(pairs, dst, a, s);
     case 34: return launch_modes<34>(pairs, dst, a, s);
     case 35: return launch_modes<35>(pairs, dst, a, s);
-    case 36: return launch_modes<36>(pairs, dst, a, s);
     case 37: return launch_modes<37>(pairs, dst, a, s);
     case 38: return launch_modes<38>(pairs, dst, a, s);
     case 39: return launch_modes<39>(pairs, dst, a, s);

@@ -57,14 +57,14 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 64, 44, 2, 1, 0, 8, 0},   // 34 two CTAs per SM: 64 keys or 44 pairs per thread
     {256, 64, 36, 2, 1, 0, 8, 0},   // 35
     // column sweep (colsweep.cuh): threads = 32 x (odd warp count), keys per thread % 8 == 4
-    {288, 36, 20, 3, 3, 12, 8, 0},  // 36 nine warps x 36 keys, three CTAs per SM, 12 ranking atomics in flight, 8-deep look-back
-    {288, 36, 20, 3, 3, 12, 4, 0},  // 37 = 36, 4-deep look-back
-    {288, 36, 20, 3, 3, 12, 12, 0}, // 38 = 36, 12-deep look-back
-    {288, 36, 20, 2, 3, 36, 8, 0},  // 39 two CTAs per SM, a whole turn in flight
-    {288, 52, 28, 2, 3, 26, 8, 0},  // 40
-    {288, 28, 20, 3, 3, 28, 8, 0},  // 41 28 keys, a whole turn in flight
-    {288, 36, 20, 3, 3, 36, 8, 0},  // 42 = 36, a whole turn in flight
-    {288, 28, 12, 4, 3, 14, 8, 0},  // 43 four CTAs per SM
+    {288, 36, 20, 3, 3, 12, 4, 0},  // 36 nine warps x 36 keys, three CTAs per SM, 12 ranking atomics and 4 look-back descriptors in flight
+    {288, 36, 20, 3, 3, 12, 8, 0},  // 37 = 36, 8-deep look-back
+    {288, 36, 20, 3, 3, 12, 2, 0},  // 38 = 36, 2-deep look-back
+    {288, 36, 20, 2, 3, 36, 4, 0},  // 39 two CTAs per SM, a whole turn in flight
+    {288, 52, 28, 2, 3, 26, 4, 0},  // 40
+    {288, 28, 20, 3, 3, 28, 4, 0},  // 41 28 keys, a whole turn in flight
+    {288, 36, 20, 3, 3, 36, 4, 0},  // 42 = 36, a whole turn in flight
+    {288, 28, 12, 4, 3, 14, 4, 0},  // 43 four CTAs per SM
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
@@ -76,11 +76,12 @@ constexpr int kColVariant = 36;  // column-sweep default geometry
 constexpr int kMinTileKeys = 2048;
 
 // true if (width, variant) is instantiated; callers fall back to variant 0 otherwise.
-// Every width also carries variant 1 (same geometry as 0, atomic rank).
+// Every width also carries variant 1 (same geometry as 0, atomic rank) and the column-sweep default
+// (kColVariant: the spec-safe kernel used when the atomic-order self test fails or safe_rank is set).
 constexpr int kBallotVariant = 16;
 constexpr int kBallotSmallVariant = 28;
 inline bool variant_available(int width, int variant) {
-    return variant == 0 || variant == 1 || variant == kBallotVariant || variant == kBallotSmallVariant ||
+    return variant == 0 || variant == 1 || variant == kBallotVariant || variant == kBallotSmallVariant || variant == kColVariant ||
            (width == 8 && variant > 0 && variant < kNumVariants);
 }
 

@@ -475,7 +475,9 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
         if (pairs) RC(s.recv_v.ensure(bytes));
         s.range_k = static_cast<const uint32_t *>(s.recv_k.p);
         s.range_v = static_cast<const uint32_t *>(s.recv_v.p);
-        if (bytes <= s.in_k.bytes) {  // the shard's input buffer is free once every partition is done
+        // the shard's input buffers are free once every partition is done (Buf::ensure only grows, and in_v
+        // is only sized by pairs calls: check it on its own)
+        if (bytes <= s.in_k.bytes && (!pairs || bytes <= s.in_v.bytes)) {
             s.sorted_k = static_cast<uint32_t *>(s.in_k.p);
             s.sorted_v = static_cast<uint32_t *>(s.in_v.p);
         } else {

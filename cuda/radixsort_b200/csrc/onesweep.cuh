@@ -558,26 +558,50 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 }
 
 // ---- self test for RANK_ATOMIC ------------------------------------------------------------------
-// Every warp replays `rounds` random digit patterns (from 1 to 256 distinct values per
-// instruction) against a private table and checks that atom.shared.add returned, for every
-// lane, the number of earlier items plus the number of LOWER lanes of the same instruction with
-// the same digit.  mismatches[0] counts violations.
+// RANK_ATOMIC needs atom.shared.add lanes of ONE warp instruction that hit the same address to be applied
+// in ascending lane order.  PTX does not promise that, so every device is tested before the mode is
+// used on it, under the conditions of the real kernel: 8 warps per CTA and three CTAs per SM; the even
+// warps replay `rounds` random digit patterns (1 to 256 distinct addresses per instruction) with a
+// DIFFERENT addend per lane (the clustered path adds run lengths) against a private table and check
+// that every lane got back the sum of the addends of all earlier instructions plus those of the LOWER
+// lanes of the same instruction with the same digit; the odd warps meanwhile hammer the banks of the
+// neighbouring table with reductions, stores and loads (the count, reorder and write-out traffic of
+// other warps).  mismatches[0] counts violations.  ~0.3 ms, once per device and process.
 template <int UNUSED>  // template only so the header can be included in several translation units
-__global__ void __launch_bounds__(256) atomic_order_selftest(uint32_t *mismatches, int rounds, uint32_t seed) {
+__global__ void __launch_bounds__(256, 3) atomic_order_selftest(uint32_t *mismatches, int rounds, uint32_t seed) {
     __shared__ __align__(1024) uint32_t table[8][256];
-    __shared__ uint32_t shadow[8][256];
+    __shared__ uint32_t shadow[4][256];
+    __shared__ uint32_t noise[8 * 1024];  // 32 KB more per CTA: three CTAs per SM like the digit-pass kernel
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; shadow[warp][i] = 0; }
-    __syncwarp();
-    const uint32_t sa_table = smem_u32(&table[warp][0]);
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&table[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 4 * 256; i += 256) (&shadow[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 8 * 1024; i += 256) noise[i] = 0;
+    __syncthreads();
     uint32_t x = seed ^ (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
+    if (warp & 1u) {
+        // interference: random-bank traffic of all three kinds next to the tables under test
+        const uint32_t sa_noise = smem_u32(noise), sa_next = smem_u32(&table[warp][0]);
+        uint32_t acc = 0;
+        for (int r = 0; r < rounds; ++r) {
+            x = x * 1664525u + 1013904223u;
+            const uint32_t o = (x >> 9) & 0x7FFCu;
+            sm_inc(sa_next | ((x >> 20) & 0x3FCu));
+            sm_st<0>(sa_noise + o, x);
+            acc += sm_ld(sa_noise + ((o * 7u) & 0x7FFCu));
+        }
+        if (acc == 0x12345678u) atomicAdd(mismatches + 1, 1u);
+        return;
+    }
+    const uint32_t sa_table = smem_u32(&table[warp][0]);
+    uint32_t *my_shadow = shadow[warp >> 1];
     uint32_t bad = 0;
     const uint32_t lt = lanemask_lt();
     for (int r = 0; r < rounds; ++r) {
         x = x * 1664525u + 1013904223u;
         const uint32_t spread = (1u << (r % 9)) - 1u;  // 1, 2, 4, ..., 256 distinct values
         const uint32_t d = (x >> 13) & spread & 255u;
-        const uint32_t got = sm_add_ret(sa_table | (d << 2), 4u) >> 2;
+        const uint32_t add = 4u * (1u + ((x >> 24) & 31u));  // 4 .. 128, different per lane
+        const uint32_t got = sm_add_ret(sa_table | (d << 2), add);
         __syncwarp();
         uint32_t peers = 0xffffffffu;  // reference rank by ballots over the 8 digit bits
 #pragma unroll
@@ -586,13 +610,24 @@ __global__ void __launch_bounds__(256) atomic_order_selftest(uint32_t *mismatche
             const uint32_t bal = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? bal : ~bal;
         }
-        const uint32_t want = shadow[warp][d] + (uint32_t)__popc(peers & lt);
+        // sum of the addends of the lower peers: walk the peer mask (<= 32 steps, warp-uniform trip count)
+        uint32_t below = 0, total = 0;
+#pragma unroll 1
+        for (uint32_t src = 0; src < 32u; ++src) {
+            const uint32_t a_src = __shfl_sync(0xffffffffu, add, src);
+            if ((peers >> src) & 1u) {
+                total += a_src;
+                if (src < lane) below += a_src;
+            }
+        }
+        (void)lt;
+        const uint32_t want = my_shadow[d] + below;
         __syncwarp();
-        if ((peers >> lane) == 1u) shadow[warp][d] += (uint32_t)__popc(peers);
+        if ((peers >> lane) == 1u) my_shadow[d] += total;
         __syncwarp();
         if (got != want) ++bad;
         if ((r & 63) == 63) {  // keep counters small
-            for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; shadow[warp][i] = 0; }
+            for (int i = lane; i < 256; i += 32) { table[warp][i] = 0; my_shadow[i] = 0; }
             __syncwarp();
         }
     }

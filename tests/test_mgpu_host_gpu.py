@@ -182,3 +182,32 @@ def test_one_heavy_value_is_split_between_shards_by_source_order(rs, oracle):
     kk = np.full(n, 7, dtype=np.uint32)
     assert np.array_equal(run(rs, kk, 8, [0, 0, 0, 0]), kk)
     assert rs.mgpu_last_stats()["imbalance"] < 1.01
+
+
+def test_small_skewed_pairs_after_large_keys_only_call(rs, oracle):
+    """Regression (round-1 advisor finding): the local sort may reuse the shard INPUT buffers as its
+    output; a large keys-only call grows only the key input buffer, so a later, smaller pairs call whose
+    received range exceeds its own shard (skewed keys) must not write values past a small value buffer."""
+    rs.mgpu_shutdown()                                   # start from empty per-shard buffers
+    devs = [0, 0, 0, 0]
+    big = oracle.generate("uniform", 1 << 22)
+    assert np.array_equal(run(rs, big, 8, devs), oracle.sort_keys(big, 8))
+    # tiny pairs call first so that the value buffers exist but are small
+    k0 = oracle.generate("uniform", 1 << 10)
+    v0 = np.arange(k0.size, dtype=np.uint32)
+    ko = np.zeros_like(k0); vo = np.zeros_like(v0)
+    rs.sort_pairs_by_devices(k0, v0, k0.size, ko, vo, 8, 512, devs)
+    # skewed pairs: the top-byte plan gives one shard far more than n/4 pairs
+    n = 1 << 18
+    k = oracle.generate("uniform", n)
+    k[: n - n // 8] = (k[: n - n // 8] & 0x00FFFFFF) | 0x7F000000
+    v = np.arange(n, dtype=np.uint32)
+    ko = np.zeros_like(k); vo = np.zeros_like(v)
+    rs.set_param("mgpu_balance_permille", 0)             # keep the bin-edge plan: one shard receives 7/8 of the pairs
+    try:
+        rs.sort_pairs_by_devices(k, v, n, ko, vo, 8, 512, devs)
+    finally:
+        rs.set_param("mgpu_balance_permille", 1200)
+    rk, rv = oracle.sort_pairs(k, v, 8)
+    assert np.array_equal(ko, rk) and np.array_equal(vo, rv)
+    assert rs.mgpu_last_stats()["imbalance"] > 2.0

@@ -230,7 +230,7 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
     assert verdict in (0, 1)
     rs.set_param("variant", 1)
     try:
-        assert rs.get_param("effective_variant") == (1 if verdict == 1 else 0)
+        assert rs.get_param("effective_variant") == (1 if verdict == 1 else 36)   # else: the spec-safe column sweep
         assert rs.get_param("atomic_rank_ok") == verdict
         for kind in ("unique16", "all_equal", "zipf"):
             n = 300007
@@ -242,6 +242,38 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
                 assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv), (kind, nbits)
     finally:
         rs.set_param("variant", -1)
+
+
+def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle):
+    """safe_rank=1 confines the library to kernels whose ranking follows from the PTX memory model: the
+    column-sweep kernel (lane-private counters, warp turns ordered by named barriers) replaces every
+    atomic-rank variant, for every digit width, for pairs and for per-bin destinations."""
+    rs.set_param("safe_rank", 1)
+    try:
+        assert rs.get_param("safe_rank") == 1
+        assert rs.get_param("effective_variant") == 36 and rs.get_param("rank_mode") == 3
+        n = (1 << 19) + 4321
+        k = oracle.generate("uniform", n)
+        z = oracle.generate("zipf", n)
+        v = np.arange(n, dtype=np.uint32)
+        for nbits in range(1, 17):
+            assert np.array_equal(dev_sort(rs, k, nbits), oracle.sort_keys(k, nbits)), nbits
+        for nbits in (8, 7, 6, 5, 4, 11):
+            ko, vo = rs.sort_pairs(to_dev(z), to_dev(v), nbits)
+            rk, rv = oracle.sort_pairs(z, v, nbits)
+            assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv), nbits
+        for kind in ("all_equal", "unique16", "sorted", "iota"):
+            kk = oracle.generate(kind, n)
+            assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), kind
+        for m in (1, 2, 31, 33, 10367, 10368, 10369, 2 * 10368 + 1):     # around the 10368-key tile
+            kk = oracle.generate("uniform", m)
+            assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), m
+        # unaligned input (no bulk copy): same answer
+        import torch
+        d = to_dev(np.concatenate([np.zeros(1, np.uint32), k]))[1:]
+        assert np.array_equal(to_host(rs.sort_keys(d, 8)), oracle.sort_keys(k, 8))
+    finally:
+        rs.set_param("safe_rank", 0)
 
 
 def test_histogram_matches_tile_table_column_sums(rs, oracle):
