@@ -398,6 +398,81 @@ def run_single(args):
     return 0
 
 
+def run_primitive(args):
+    """--workload scan|hist: the two reusable primitives the reference treats as stages of their own
+    (Docs/Snippets/PrefixSum-WorkEfficient.cu:229 scanByDevice, Docs/Snippets/Histogram.cu:17), device-resident,
+    CUDA events, input larger than L2 when log2n >= 26 (else L2 is flushed between steps by a 256 MiB write)."""
+    import torch
+
+    import cuda.radixsort_b200 as rs
+
+    torch.cuda.set_device(0)
+    rs.load()
+    n = 1 << args.log2n
+    what = args.workload
+    ref = None
+    if not args.no_gpu_baselines:
+        ref = _run_json([sys.executable, os.path.join(ROOT, "tools", "ref_primitive_time.py"), "--what", what,
+                         "--log2n", str(min(args.log2n, 24))], timeout=300)
+    keys = rs.generate("uniform", n)
+    if what == "scan":
+        x = (keys & 3).contiguous()                          # rand() & 0b11 like the snippet's main()
+        out = torch.empty_like(x)
+        ws = rs.Workspace("cuda")
+        step = lambda: rs.exclusive_scan(x, out=out, workspace=ws)      # noqa: E731
+        bytes_per_elem, kernel = 8, "exclusive_scan_kernel"
+    else:
+        x = keys
+        ws = rs.Workspace("cuda")
+        holder = {}
+
+        def step():
+            holder["h"] = rs.histogram(x, 0, 8, workspace=ws)
+        bytes_per_elem, kernel = 4, "hist_kernel"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if n * 4 < (512 << 20) else None
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = rs.launch_count()
+    sampler = ClockSampler(0).start()
+    times = []
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    clocks = sampler.stop()
+    launches = rs.launch_count() - launches0
+    ms = sum(times) / len(times)
+    # correctness of what was timed
+    if what == "scan":
+        want = torch.cumsum(x.to(torch.int64), 0) - x.to(torch.int64)
+        assert torch.equal(out.to(torch.int64) & 0xFFFFFFFF, want & 0xFFFFFFFF), "scan differs from torch.cumsum"
+    else:
+        want = torch.bincount((x & 255).to(torch.int64), minlength=256)
+        assert torch.equal(holder["h"].to(torch.int64), want), "histogram differs from torch.bincount"
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_elem * n / (ms * 1e-3) / 1e9
+    line = {
+        "metric": f"uint32 elements/sec ({'exclusive scan' if what == 'scan' else '256-bin histogram'})",
+        "value": n / (ms * 1e-3), "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": f"{what} of 2^{args.log2n} uint32, device-resident, 1 B200", "n": n,
+                   "l2": "input larger than L2" if flush is None else "L2 flushed between steps (256 MiB write)"},
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_elem * n, "avg_launch_ms": ms},
+        "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None, "e2e": None,
+        "gpu_reference": ref,
+        "scan_variant": rs.get_param("scan_variant") if what == "scan" else None,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def bit_exact_sharded_check(rs, mgpu, dist, args, rank, world, log2n=24):
     """The sharded sort against the oracle (checker only) at a size the CPU sort finishes in a second:
     concatenated shards == sortByHost of the whole input (Baseline1.cu:15-64)."""
@@ -566,7 +641,7 @@ def main():
     ap.add_argument("--balance-threshold", type=float, default=1.2,
                     help="multi-GPU: bin-edge splitters leaving a shard above this x mean switch to value splitters")
     ap.add_argument("--workload", default="uniform",
-                    choices=["uniform", "zipf", "unique16", "all_equal", "sorted", "reversed", "pairs"])
+                    choices=["uniform", "zipf", "unique16", "all_equal", "sorted", "reversed", "pairs", "scan", "hist"])
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--log2n-multi", type=int, default=32)
     ap.add_argument("--nbits", type=int, default=8)
@@ -581,6 +656,7 @@ def main():
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-narrow", action="store_true")
     ap.add_argument("--narrow-variant", type=int, default=None)
+    ap.add_argument("--scan-variant", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -592,6 +668,11 @@ def main():
     if args.narrow_variant is not None:
         import cuda.radixsort_b200 as rs
         rs.set_param("narrow_variant", args.narrow_variant)
+    if args.scan_variant is not None:
+        import cuda.radixsort_b200 as rs
+        rs.set_param("scan_variant", args.scan_variant)
+    if args.workload in ("scan", "hist"):
+        return run_primitive(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 or args.gpus > 1:
         if world == 1:

@@ -36,6 +36,7 @@ struct Params {
     std::atomic<int> hist_ctas_per_sm{2};
     std::atomic<int> narrow_variant{-1}; // digit passes of <= 3 bits: -1 = kBallotVariant
     std::atomic<int> safe_rank{0};       // 1 = only kernels whose ranking follows from the PTX memory model
+    std::atomic<int> scan_variant{8};    // tile geometry of b200sort_exclusive_scan (scan.cuh: kScanGeom)
 } g_params;
 
 // Per CUDA ordinal: the sm_100 check, the SM count and the verdict of the RANK_ATOMIC self test
@@ -591,6 +592,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.safe_rank = value;
         return 0;
     }
+    if (!strcmp(name, "scan_variant")) {
+        if (value < 0 || value >= kScanNumVariants) return B200SORT_EINVAL;
+        g_params.scan_variant = value;
+        return 0;
+    }
     return B200SORT_EINVAL;
 }
 
@@ -602,6 +608,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "mgpu_balance_permille")) return g_mgpu_balance_permille.load();
     if (!strcmp(name, "num_variants")) return kNumVariants;
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
+    if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
     if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
     if (!strcmp(name, "effective_variant")) return check_device() ? std::max<int>(g_params.variant.load(), 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
@@ -753,7 +760,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
 }
 
 size_t b200sort_scan_temp_bytes(uint64_t n) {
-    return align_up(((n + kScanTile - 1) / kScanTile) * sizeof(uint64_t), 256) + 256;
+    return align_up(((n + kScanMinTile - 1) / kScanMinTile) * sizeof(uint64_t), 256) + 256;
 }
 
 int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp, size_t temp_bytes,
@@ -761,7 +768,9 @@ int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, v
     if (n == 0) return 0;
     if (!d_in || !d_out) return fail(B200SORT_EINVAL, "null buffer");
     if (((uintptr_t)d_in | (uintptr_t)d_out) & 15u) return fail(B200SORT_EINVAL, "scan buffers must be 16-byte aligned");
-    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    const int sv = g_params.scan_variant;
+    const uint64_t tile_elems = (uint64_t)scan_tile(sv);
+    const uint64_t tiles = (n + tile_elems - 1) / tile_elems;
     if (tiles > 0x7FFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
     if (!d_temp || ((uintptr_t)d_temp & 255u) || temp_bytes < b200sort_scan_temp_bytes(n))
         return fail(B200SORT_ETEMP, "temp storage");
@@ -770,7 +779,18 @@ int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, v
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemsetAsync(d_temp, 0, tiles * sizeof(uint64_t), s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    exclusive_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, s>>>(d_in, d_out, n, static_cast<uint64_t *>(d_temp));
+    uint64_t *desc = static_cast<uint64_t *>(d_temp);
+    switch (sv) {
+    case 0: exclusive_scan_kernel<256, 4><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
+    case 1: exclusive_scan_kernel<512, 4><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc); break;
+    case 2: exclusive_scan_kernel<512, 8><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc); break;
+    case 3: exclusive_scan_kernel<1024, 4><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc); break;
+    case 4: exclusive_scan_kernel<1024, 8><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc); break;
+    case 5: exclusive_scan_kernel<128, 8><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
+    case 6: exclusive_scan_kernel<256, 8><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
+    case 7: exclusive_scan_kernel<256, 16><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
+    default: exclusive_scan_kernel<128, 16><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
+    }
     CU(cudaGetLastError());
     return 0;
 }

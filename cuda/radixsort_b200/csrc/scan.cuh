@@ -9,9 +9,12 @@
 
 namespace b200sort {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanVecs = 4;                                  // uint4 per thread
-constexpr int kScanTile = kScanThreads * kScanVecs * 4;       // 4096 elements per tile
+// Tile geometries (threads x uint4 per thread); the host picks one with scan_tile(variant).  The smallest
+// tile bounds the descriptor array.
+constexpr int kScanNumVariants = 9;
+constexpr int kScanGeom[kScanNumVariants][2] = {{256, 4}, {512, 4}, {512, 8}, {1024, 4}, {1024, 8}, {128, 8}, {256, 8}, {256, 16}, {128, 16}};
+constexpr int kScanMinTile = 256 * 4 * 4;
+inline int scan_tile(int variant) { return kScanGeom[variant][0] * kScanGeom[variant][1] * 4; }
 
 // descriptor: {status in the high word | value in the low word}; 0 = not ready
 constexpr uint64_t kScanAggregate = 1ull << 32;
@@ -28,8 +31,10 @@ __device__ __forceinline__ void st_relaxed_gpu64(uint64_t *p, uint64_t v) {
 
 // desc: one zeroed uint64 per tile.  Requires in/out 16-byte aligned (checked by the host); the
 // last partial tile is handled with scalar accesses.
+template <int kScanThreads, int kScanVecs>
 __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t *in, uint32_t *out, uint64_t n,
                                                                        uint64_t *desc) {
+    constexpr int kScanTile = kScanThreads * kScanVecs * 4;
     __shared__ uint32_t s_warp_tot[32];
     __shared__ uint32_t s_prefix;
     __shared__ uint32_t s_total;
@@ -99,14 +104,17 @@ __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint
             for (;;) {
                 const int64_t mine = t - (int64_t)lane;
                 uint64_t d = kScanInclusive;  // before tile 0: an inclusive prefix of zero
-                if (mine >= 0) {
-                    do {
-                        d = ld_relaxed_gpu64(desc + mine);
-                    } while ((d >> 32) == 0);
+                // every lane reads its predecessor once per poll; only the descriptors NEARER than the nearest
+                // inclusive one have to be ready, so the warp re-polls until that prefix is complete
+                uint32_t incl_mask, ready_mask, upto;
+                for (;;) {
+                    if (mine >= 0) d = ld_relaxed_gpu64(desc + mine);
+                    incl_mask = __ballot_sync(0xffffffffu, (d >> 32) == 2u);
+                    ready_mask = __ballot_sync(0xffffffffu, (d >> 32) != 0u);
+                    upto = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 31u;
+                    const uint32_t need = (upto == 31u) ? 0xffffffffu : ((2u << upto) - 1u);
+                    if ((ready_mask & need) == need) break;
                 }
-                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d >> 32) == 2u);
-                // lanes up to and including the nearest inclusive descriptor contribute
-                const uint32_t upto = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 31u;
                 const uint32_t part = (lane <= upto) ? (uint32_t)d : 0u;
                 excl += __reduce_add_sync(0xffffffffu, part);
                 if (incl_mask) break;

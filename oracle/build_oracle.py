@@ -23,6 +23,9 @@ REF_ROOT = os.environ.get("B200SORT_REFERENCE", "/root/reference")
 REF_DIR = os.path.join(HERE, "_ref")
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_FILES = ("Baseline1", "Baseline4", "Parallel7")
+# the reference's standalone kernel studies (Docs/Snippets), used only as same-box bars for the scan and
+# histogram primitives in bench.py --workload scan|hist
+SNIPPET_FILES = {"PrefixSum": "PrefixSum-WorkEfficient", "Histogram": "Histogram"}
 
 
 def _newer(target: str, *sources: str) -> bool:
@@ -45,7 +48,7 @@ def ref_so(name: str) -> str:
     return os.path.join(REF_DIR, f"libref_{name.lower()}.so")
 
 
-def build_reference(force: bool = False, files=REF_FILES) -> list[str]:
+def build_reference(force: bool = False, files=REF_FILES + tuple(SNIPPET_FILES)) -> list[str]:
     """Compile the reference's own .cu files into oracle/_ref/ (skipped without the sources)."""
     src_dir = os.path.join(REF_ROOT, "SourceCode")
     if not os.path.isdir(src_dir):
@@ -54,12 +57,17 @@ def build_reference(force: bool = False, files=REF_FILES) -> list[str]:
     os.makedirs(REF_DIR, exist_ok=True)
     built = []
     for name in files:
-        src = os.path.join(src_dir, f"{name}.cu")
+        if name in SNIPPET_FILES:
+            inc = os.path.join(REF_ROOT, "Docs", "Snippets")
+            src = os.path.join(inc, f"{SNIPPET_FILES[name]}.cu")
+        else:
+            inc = src_dir
+            src = os.path.join(src_dir, f"{name}.cu")
         out = ref_so(name)
         if force or not _newer(out, src):
             cmd = [nvcc, "-O2", "-std=c++17", "-w",
                    "-gencode", "arch=compute_100a,code=sm_100a",
-                   "-I", src_dir, "-Dmain=ref_main",
+                   "-I", inc, "-Dmain=ref_main",
                    "-Xcompiler", "-fPIC", "-shared", "-o", out, src]
             subprocess.run(cmd, check=True)
         built.append(out)

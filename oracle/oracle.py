@@ -19,7 +19,7 @@ from . import build_oracle as _build
 
 __all__ = [
     "GEN_KINDS", "fnv1a64", "generate", "glibc_rand_keys", "is_sorted", "multiset_fingerprint",
-    "num_passes", "ref_available", "ref_sort_by_device", "ref_sort_by_host",
+    "num_passes", "ref_available", "ref_sort_by_device", "ref_sort_by_host", "ref_scan_by_device", "ref_histogram_by_device",
     "ref_sort_by_host_parallel_algorithm", "sort_keys", "sort_pairs", "tile_table", "zipf_cdf",
 ]
 
@@ -213,4 +213,41 @@ def ref_sort_by_device(keys, nbits: int = 8, block_size: int = 512) -> np.ndarra
     k = _u32(keys)
     out = np.empty_like(k)
     fn(_p(k), k.size, _p(out), nbits, block_size)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# The reference's standalone kernel studies (Docs/Snippets), compiled where they lie: same-box bars for the
+# scan and histogram primitives (bench.py --workload scan|hist).  Both need a GPU and print their own "Time:".
+
+def ref_scan_by_device(values, implementation: int = 2, block_size: int = 512) -> np.ndarray:
+    """void scanByDevice(const int*, int, int*, Implementation, int) -- Docs/Snippets/PrefixSum-WorkEfficient.cu:229
+    (exclusive scan; implementation 1 = BY_DEVICE, 2 = BY_DEVICE_UNROLL2, 3 = BY_DEVICE_UNROLL2_PAD; host arrays,
+    cudaMalloc + H2D + kernels + host scan of the block sums + D2H inside)."""
+    lib = _ref("PrefixSum")
+    if lib is None:
+        raise RuntimeError("oracle/_ref/libref_prefixsum.so not built")
+    fn = lib._Z12scanByDevicePKiiPi14Implementationi
+    i32p = C.POINTER(C.c_int32)
+    fn.argtypes = [i32p, C.c_int, i32p, C.c_int, C.c_int]
+    fn.restype = None
+    x = np.ascontiguousarray(values, dtype=np.int32)
+    out = np.empty_like(x)
+    fn(x.ctypes.data_as(i32p), x.size, out.ctypes.data_as(i32p), implementation, block_size)
+    return out
+
+
+def ref_histogram_by_device(values, num_bins: int, block_size: int = 512) -> np.ndarray:
+    """void histogram(const int*, int, int*, int numBins, Implementation = BY_DEVICE, int blockSize) --
+    Docs/Snippets/Histogram.cu:35 (values must be < numBins; host arrays, everything inside)."""
+    lib = _ref("Histogram")
+    if lib is None:
+        raise RuntimeError("oracle/_ref/libref_histogram.so not built")
+    fn = lib._Z9histogramPKiiPii14Implementationi
+    i32p = C.POINTER(C.c_int32)
+    fn.argtypes = [i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int]
+    fn.restype = None
+    x = np.ascontiguousarray(values, dtype=np.int32)
+    out = np.zeros(num_bins, dtype=np.int32)
+    fn(x.ctypes.data_as(i32p), x.size, out.ctypes.data_as(i32p), num_bins, 1, block_size)
     return out
