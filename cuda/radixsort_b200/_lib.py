@@ -33,6 +33,7 @@ SIGNATURES = {
     "b200sort_pairs_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int]),
     "b200sort_shutdown": (C.c_int, []),
+    "b200sort_warmup": (C.c_int, [C.c_uint64, C.c_int]),
     "b200sort_route": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "b200sort_mgpu_keys_host": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,

@@ -27,7 +27,7 @@ from ._lib import RadixSortError
 
 __all__ = [
     "Implementation", "SORT_BY_HOST", "SORT_BY_THRUST", "SORT_BY_DEVICE", "sort", "sortByDevice",
-    "sort_by_device", "sort_pairs_by_device", "sort_by_devices", "sort_pairs_by_devices", "mgpu_last_stats", "mgpu_shutdown",
+    "sort_by_device", "sort_pairs_by_device", "sort_by_devices", "sort_pairs_by_devices", "mgpu_last_stats", "mgpu_shutdown", "warmup",
     "Workspace", "sort_keys", "sort_pairs", "histogram",
     "digit_pass", "route", "exclusive_scan", "generate", "verify", "temp_bytes", "algorithmic_bytes", "num_passes",
     "tile_keys", "set_param", "get_param", "profile_enable", "profile_read", "launch_count",
@@ -393,6 +393,12 @@ def profile_read(capacity: int = 4096) -> list[tuple[int, float]]:
 
 def launch_count() -> int:
     return int(_lib.load().b200sort_launch_count())
+
+
+def warmup(max_n: int, pairs: bool = False) -> None:
+    """Pays the one-time costs of the host-pointer entry points (buffers, staging, self test, kernel loads) now:
+    b200sort_warmup."""
+    _lib.check(_lib.load().b200sort_warmup(int(max_n), int(bool(pairs))))
 
 
 def mgpu_shutdown() -> None:

@@ -36,6 +36,7 @@ struct Params {
     std::atomic<int> hist_ctas_per_sm{2};
     std::atomic<int> narrow_variant{-1}; // digit passes of <= 3 bits: -1 = kBallotVariant
     std::atomic<int> safe_rank{0};       // 1 = only kernels whose ranking follows from the PTX memory model
+    std::atomic<int> host_overlap{1};    // host-pointer path: chunked upload + MSD split + per-bucket download
     std::atomic<int> scan_variant{8};    // tile geometry of b200sort_exclusive_scan (scan.cuh: kScanGeom)
 } g_params;
 
@@ -100,13 +101,15 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // 32 % nBits != 0, exactly like the loop at SourceCode/Baseline1.cu:30).
 // nBits 9..16: each reference digit is split into a low sub-digit of ceil(nBits/2) bits and a
 // high sub-digit of the remaining bits, both stable -> same order as one wide pass.
-bool build_pass_list(int nbits, PassList &pl) {
-    if (nbits < 1 || nbits > 16) return false;
+// key_bits < 32: the keys are known to agree in their bits >= key_bits (a bucket of an MSD partition), so
+// the digits above are skipped.
+bool build_pass_list(int nbits, PassList &pl, int key_bits = 32) {
+    if (nbits < 1 || nbits > 16 || key_bits < 1 || key_bits > 32) return false;
     const int lo = nbits <= kMaxRadixBits ? nbits : (nbits + 1) / 2;
     pl.width = lo;
     pl.count = 0;
-    for (int s = 0; s < 32; s += nbits) {
-        const int w = std::min(nbits, 32 - s);
+    for (int s = 0; s < key_bits; s += nbits) {
+        const int w = std::min(nbits, key_bits - s);
         pl.shift[pl.count] = (uint8_t)s;
         pl.bits[pl.count] = (uint8_t)std::min(w, lo);
         ++pl.count;
@@ -289,10 +292,10 @@ bool ranges_overlap(const void *a, const void *b, uint64_t bytes) {
 
 // ---- the sort ------------------------------------------------------------------------------------
 int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kout, uint32_t *vout,
-             void *temp, size_t temp_bytes, int nbits, cudaStream_t stream) {
+             void *temp, size_t temp_bytes, int nbits, cudaStream_t stream, int key_bits = 32) {
     const bool pairs = (vin != nullptr) || (vout != nullptr);
     PassList pl;
-    if (!build_pass_list(nbits, pl)) return fail(B200SORT_EINVAL, "nBits must be in 1..16");
+    if (!build_pass_list(nbits, pl, key_bits)) return fail(B200SORT_EINVAL, "nBits must be in 1..16");
     if (n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
     if (n == 0) return B200SORT_OK;
     if (!kin || !kout || (pairs && (!vin || !vout))) return fail(B200SORT_EINVAL, "null buffer");
@@ -327,7 +330,7 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
     h.zero_ptr = reinterpret_cast<uint4 *>(desc);
     h.zero_vecs = L.desc_bytes / 16;
     h.passes = pl;
-    CU(launch_hist(pl.width, nbits <= kMaxRadixBits, h, hist_grid(n, pl.count, pl.width), stream));
+    CU(launch_hist(pl.width, nbits <= kMaxRadixBits && key_bits == 32, h, hist_grid(n, pl.count, pl.width), stream));
     CU(profile_mark(stream, 0));
 
     const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
@@ -378,6 +381,10 @@ struct HostCtx {
     void *stage[kStageSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr};
     CopyPool *pool = nullptr;
+    // overlapped path (sort_host_overlapped): a copy stream, one event per upload chunk / bucket, 16 host counters
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    uint32_t *h_small = nullptr;  // pinned
 } g_host;
 
 int ensure_host_ctx(size_t bytes) {
@@ -411,6 +418,22 @@ int ensure_staging() {
     return 0;
 }
 
+int ensure_overlap_ctx(size_t num_events) {
+    if (!g_host.copy_stream) CU(cudaStreamCreateWithFlags(&g_host.copy_stream, cudaStreamNonBlocking));
+    while (g_host.events.size() < num_events) {
+        cudaEvent_t ev;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        g_host.events.push_back(ev);
+    }
+    if (!g_host.h_small) {
+        if (cudaMallocHost(&g_host.h_small, 4096) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200SORT_ENOMEM, "cudaMallocHost");
+        }
+    }
+    return 0;
+}
+
 bool is_pageable(const void *p) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
@@ -420,30 +443,41 @@ bool is_pageable(const void *p) {
     return attr.type == cudaMemoryTypeUnregistered;
 }
 
-// host -> device, asynchronous on g_host.stream as far as the source allows
-int upload(void *d_dst, const void *h_src, size_t bytes) {
-    cudaStream_t s = g_host.stream;
-    if (bytes < (8u << 20) || !is_pageable(h_src)) {
-        CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
-        return 0;
+// host -> device on stream `s`, asynchronous as far as the source allows, in chunks of kStageChunk bytes;
+// after_chunk(offset, length) is called once the copy of a chunk has been enqueued (the overlapped path
+// records an event there and queues the chunk's histogram on the compute stream).
+template <typename F>
+int upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s, F after_chunk) {
+    const bool staged = bytes >= (8u << 20) && is_pageable(h_src);
+    if (staged) {
+        int rc = ensure_staging();
+        if (rc) return rc;
     }
-    int rc = ensure_staging();
-    if (rc) return rc;
     size_t off = 0;
     for (int c = 0; off < bytes; ++c, off += kStageChunk) {
         const int slot = c % kStageSlots;
         const size_t len = std::min(kStageChunk, bytes - off);
-        CU(cudaEventSynchronize(g_host.stage_ev[slot]));  // the DMA that last used this slot is done
-        g_host.pool->copy(g_host.stage[slot], static_cast<const char *>(h_src) + off, len);
-        CU(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, g_host.stage[slot], len, cudaMemcpyHostToDevice, s));
-        CU(cudaEventRecord(g_host.stage_ev[slot], s));
+        const void *src = static_cast<const char *>(h_src) + off;
+        if (staged) {
+            CU(cudaEventSynchronize(g_host.stage_ev[slot]));  // the DMA that last used this slot is done
+            g_host.pool->copy(g_host.stage[slot], src, len);
+            src = g_host.stage[slot];
+        }
+        CU(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, src, len, cudaMemcpyHostToDevice, s));
+        if (staged) CU(cudaEventRecord(g_host.stage_ev[slot], s));
+        int rc = after_chunk(off, len);
+        if (rc) return rc;
     }
     return 0;
 }
+int upload(void *d_dst, const void *h_src, size_t bytes) {
+    return upload(d_dst, h_src, bytes, g_host.stream, [](size_t, size_t) { return 0; });
+}
 
-// device -> host; returns after the data is in h_dst when staging is used
-int download(void *h_dst, const void *d_src, size_t bytes) {
-    cudaStream_t s = g_host.stream;
+// device -> host on stream `s`; returns after the data is in h_dst when staging is used
+int download(void *h_dst, const void *d_src, size_t bytes, cudaStream_t s = nullptr) {
+    if (!s) s = g_host.stream;
+    if (bytes == 0) return 0;
     if (bytes < (8u << 20) || !is_pageable(h_dst)) {
         CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
         return 0;
@@ -471,6 +505,122 @@ int download(void *h_dst, const void *d_src, size_t bytes) {
     return 0;
 }
 
+// ---- host-pointer path with the copies overlapped ----------------------------------
+// sortByDevice brackets its digit loop with one H2D and one D2H of the whole array (Parallel7.cu:549, :624).
+// Here, for large arrays:
+//   * the upload runs in chunks on a copy stream; the histogram of the top kMsdBits bits of every chunk is
+//     accumulated on the compute stream as soon as the chunk has landed (K1 on a key range);
+//   * one stable digit pass on those top bits splits the keys into 2^kMsdBits buckets (MSD step);
+//   * every bucket is then sorted on its remaining 32 - kMsdBits bits (LSD), back into the input buffer, and
+//     downloaded on the copy stream while the next bucket is being sorted.
+// The order is the same (a stable MSD split followed by stable LSD sorts of the buckets is a stable sort);
+// the extra digit pass hides behind the download, which no longer waits for the whole sort.
+constexpr int kMsdBits = 4;
+constexpr uint64_t kOverlapMinKeys = 1ull << 24;
+
+int sort_host_overlapped(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t *hk_out, uint32_t *hv_out,
+                         bool pairs, uint32_t *dk_in, uint32_t *dk_out, uint32_t *dv_in, uint32_t *dv_out, void *temp,
+                         size_t temp_bytes, int nbits) {
+    constexpr int B = 1 << kMsdBits;
+    const size_t bytes = (size_t)n * 4;
+    const size_t chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    int rc = ensure_overlap_ctx(chunks + B + 2);
+    if (rc) return rc;
+    cudaStream_t s = g_host.stream, sc = g_host.copy_stream;
+
+    const int variant = effective_variant(kMsdBits, pairs);
+    const int tile = tile_keys(variant, pairs);
+    const Layout L = make_layout(n, 1, kMsdBits, pairs, false, tile, g_params.portion_tiles);
+    if (temp_bytes < L.total) return fail(B200SORT_ETEMP, "temp storage too small");
+    char *base = static_cast<char *>(temp);
+    uint32_t *done = reinterpret_cast<uint32_t *>(base + L.off_done);  // [0] counts the CTAs of the LAST chunk
+    uint32_t *ghist = reinterpret_cast<uint32_t *>(base + L.off_ghist);
+    uint32_t *bin_base = reinterpret_cast<uint32_t *>(base + L.off_bin_base);
+    uint32_t *desc = reinterpret_cast<uint32_t *>(base + L.off_desc);
+    CU(cudaMemsetAsync(base, 0, L.header_bytes, s));
+    CU(cudaMemsetAsync(done + 1, 0x40, 4, s));  // [1]: a counter that never reaches a grid size (earlier chunks)
+
+    // ---- upload + per-chunk histogram
+    size_t c = 0;
+    rc = upload(dk_in, hk_in, bytes, sc, [&](size_t off, size_t len) -> int {
+        cudaEvent_t ev = g_host.events[c];
+        CU(cudaEventRecord(ev, sc));
+        CU(cudaStreamWaitEvent(s, ev, 0));
+        const bool last = (off + len == bytes);
+        HistArgs h{};
+        h.keys = dk_in + off / 4;
+        h.n = len / 4;
+        h.ghist = ghist;
+        h.bin_base = bin_base;
+        h.done = last ? done : done + 1;  // only the last chunk's last CTA turns the histogram into bin bases
+        h.zero_ptr = last ? reinterpret_cast<uint4 *>(desc) : nullptr;
+        h.zero_vecs = last ? L.desc_bytes / 16 : 0;
+        h.passes.count = 1;
+        h.passes.width = kMsdBits;
+        h.passes.shift[0] = (uint8_t)(32 - kMsdBits);
+        h.passes.bits[0] = (uint8_t)kMsdBits;
+        CU(launch_hist(kMsdBits, false, h, hist_grid(h.n, 1, kMsdBits), s));
+        ++c;
+        return 0;
+    });
+    if (rc) return rc;
+    if (pairs) {
+        if ((rc = upload(dv_in, hv_in, bytes, sc, [](size_t, size_t) { return 0; })) != 0) return rc;
+        CU(cudaEventRecord(g_host.events[chunks], sc));
+        CU(cudaStreamWaitEvent(s, g_host.events[chunks], 0));
+    }
+    CU(cudaMemcpyAsync(g_host.h_small, ghist, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+
+    // ---- MSD step: one stable digit pass on the top kMsdBits bits, dk_in -> dk_out
+    const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
+    for (uint64_t q = 0; q < L.portions; ++q) {
+        const uint64_t first = q * portion_keys;
+        const uint64_t count = std::min<uint64_t>(portion_keys, n - first);
+        PassArgs a{};
+        a.keys_in = dk_in + first;
+        a.vals_in = pairs ? dv_in + first : nullptr;
+        a.keys_out = dk_out;
+        a.vals_out = pairs ? dv_out : nullptr;
+        a.bin_base = bin_base + (q & 1) * L.bins;
+        a.carry_out = (q + 1 < L.portions) ? bin_base + ((q + 1) & 1) * L.bins : nullptr;
+        a.desc = desc + (size_t)q * L.portion_tiles * L.bins;
+        a.ticket = reinterpret_cast<uint32_t *>(base + L.off_tickets) + q;
+        a.bin_dst = nullptr;
+        a.n = (uint32_t)count;
+        a.num_tiles = (uint32_t)((count + tile - 1) / tile);
+        a.shift = 32 - kMsdBits;
+        a.mask = B - 1;
+        a.parity = 0;
+        CU(launch_pass(kMsdBits, variant, pairs, false, a, s));
+    }
+    CU(cudaStreamSynchronize(s));  // bucket sizes are on the host now (the upload is complete as well)
+
+    // ---- per bucket: LSD sort on the remaining bits into the input buffer, then download
+    uint64_t offs[B + 1];
+    offs[0] = 0;
+    for (int b = 0; b < B; ++b) offs[b + 1] = offs[b] + g_host.h_small[b];
+    if (offs[B] != n) return fail(B200SORT_EINVAL, "internal: bucket sizes do not add up");
+    for (int b = 0; b < B; ++b) {
+        const uint64_t cnt = offs[b + 1] - offs[b];
+        if (cnt) {
+            rc = run_sort(dk_out + offs[b], pairs ? dv_out + offs[b] : nullptr, cnt, dk_in + offs[b],
+                          pairs ? dv_in + offs[b] : nullptr, temp, temp_bytes, nbits, s, 32 - kMsdBits);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(g_host.events[chunks + 1 + b], s));
+    }
+    for (int b = 0; b < B; ++b) {
+        const uint64_t cnt = offs[b + 1] - offs[b];
+        if (!cnt) continue;
+        CU(cudaStreamWaitEvent(sc, g_host.events[chunks + 1 + b], 0));
+        if ((rc = download(hk_out + offs[b], dk_in + offs[b], cnt * 4, sc)) != 0) return rc;
+        if (pairs && (rc = download(hv_out + offs[b], dv_in + offs[b], cnt * 4, sc)) != 0) return rc;
+    }
+    CU(cudaStreamSynchronize(sc));
+    CU(cudaStreamSynchronize(s));
+    return B200SORT_OK;
+}
+
 int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t *hk_out,
               uint32_t *hv_out, int nbits, int block_size, bool pairs) {
     PassList pl;
@@ -496,6 +646,9 @@ int sort_host(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t n, uint32_t
     void *temp = b + arrays * arr;
     cudaStream_t s = g_host.stream;
 
+    if (n >= kOverlapMinKeys && nbits == 8 && g_params.host_overlap)
+        return sort_host_overlapped(hk_in, hv_in, n, hk_out, hv_out, pairs, dk_in, dk_out, dv_in, dv_out, temp,
+                                    temp_bytes, nbits);
     if ((rc = upload(dk_in, hk_in, (size_t)n * 4)) != 0) return rc;
     if (pairs && (rc = upload(dv_in, hv_in, (size_t)n * 4)) != 0) return rc;
     rc = run_sort(dk_in, dv_in, n, dk_out, dv_out, temp, temp_bytes, nbits, s);
@@ -592,6 +745,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.safe_rank = value;
         return 0;
     }
+    if (!strcmp(name, "host_overlap")) {
+        if (value != 0 && value != 1) return B200SORT_EINVAL;
+        g_params.host_overlap = value;
+        return 0;
+    }
     if (!strcmp(name, "scan_variant")) {
         if (value < 0 || value >= kScanNumVariants) return B200SORT_EINVAL;
         g_params.scan_variant = value;
@@ -609,6 +767,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "num_variants")) return kNumVariants;
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
     if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
+    if (!strcmp(name, "host_overlap")) return g_params.host_overlap;
     if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
     if (!strcmp(name, "effective_variant")) return check_device() ? std::max<int>(g_params.variant.load(), 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
@@ -637,6 +796,37 @@ int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, ui
     return sort_host(h_keys_in, h_vals_in, n, h_keys_out, h_vals_out, nBits, blockSize, true);
 }
 
+int b200sort_warmup(uint64_t max_n, int pairs) {
+    if (max_n > 0xFFFFFFFFull) return fail(B200SORT_ETOOBIG, "n");
+    int rc = check_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    run_selftest();  // decides the rank mode of this device once
+    const size_t arr = align_up((size_t)std::max<uint64_t>(max_n, 1) * 4, 256);
+    rc = ensure_host_ctx((pairs ? 4 : 2) * arr + temp_upper_bound(std::max<uint64_t>(max_n, 1), 8, pairs != 0));
+    if (rc) return rc;
+    if ((rc = ensure_staging()) != 0) return rc;
+    if ((rc = ensure_overlap_ctx(((size_t)max_n * 4 + kStageChunk - 1) / kStageChunk + (1 << kMsdBits) + 2)) != 0) return rc;
+    // load the kernels of the default path: one tiny sort of each kind through the device buffers
+    char *b = static_cast<char *>(g_host.d_buf);
+    uint32_t *k_in = reinterpret_cast<uint32_t *>(b), *k_out = reinterpret_cast<uint32_t *>(b + arr);
+    void *temp = b + (pairs ? 4 : 2) * arr;
+    const size_t temp_bytes = temp_upper_bound(std::max<uint64_t>(max_n, 1), 8, pairs != 0);
+    const uint64_t m = std::min<uint64_t>(std::max<uint64_t>(max_n, 1), 1u << 16);
+    CU(cudaMemsetAsync(k_in, 0, m * 4, g_host.stream));
+    if ((rc = run_sort(k_in, nullptr, m, k_out, nullptr, temp, temp_bytes, 8, g_host.stream)) != 0) return rc;
+    if (pairs) {
+        uint32_t *v_in = reinterpret_cast<uint32_t *>(b + 2 * arr), *v_out = reinterpret_cast<uint32_t *>(b + 3 * arr);
+        CU(cudaMemsetAsync(v_in, 0, m * 4, g_host.stream));
+        if ((rc = run_sort(k_in, v_in, m, k_out, v_out, temp, temp_bytes, 8, g_host.stream)) != 0) return rc;
+    }
+    if (max_n >= kOverlapMinKeys) {  // the MSD step of the overlapped host path uses the 4-bit kernels
+        if ((rc = run_sort(k_in, nullptr, m, k_out, nullptr, temp, temp_bytes, 4, g_host.stream)) != 0) return rc;
+    }
+    CU(cudaStreamSynchronize(g_host.stream));
+    return B200SORT_OK;
+}
+
 int b200sort_shutdown(void) {
     b200sort_mgpu_shutdown();
     std::lock_guard<std::mutex> lock(g_host.mu);
@@ -653,6 +843,12 @@ int b200sort_shutdown(void) {
     g_host.pool = nullptr;
     if (g_host.stream) cudaStreamDestroy(g_host.stream);
     g_host.stream = nullptr;
+    if (g_host.copy_stream) cudaStreamDestroy(g_host.copy_stream);
+    g_host.copy_stream = nullptr;
+    for (cudaEvent_t ev : g_host.events) cudaEventDestroy(ev);
+    g_host.events.clear();
+    if (g_host.h_small) cudaFreeHost(g_host.h_small);
+    g_host.h_small = nullptr;
     for (cudaEvent_t ev : g_events) cudaEventDestroy(ev);
     g_events.clear();
     g_event_tags.clear();

@@ -53,6 +53,11 @@ enum {
  * (pageable or pinned); h_in is not modified; h_out is fully overwritten; h_out == h_in is
  * allowed.  Blocking.  Device buffers are cached by the library between calls and released
  * by b200sort_shutdown().  One call at a time per process (internally serialised).
+ * Where sortByDevice copies the whole array in, sorts, and copies it out (Parallel7.cu:549, :624),
+ * arrays of 2^24 keys and more with 8-bit digits are pipelined: chunked upload with the histogram of the
+ * top 4 bits accumulated per chunk, one stable digit pass on those bits (16 buckets), then every bucket
+ * is sorted on its low 28 bits and downloaded while the next one is being sorted -- the same stable
+ * order (b200sort_set_param("host_overlap", 0) restores the single-shot form).
  */
 int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nBits,
                        int blockSize);
@@ -61,6 +66,13 @@ int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nB
  * equal keys keep their input order. */
 int b200sort_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_in, uint64_t n,
                         uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits, int blockSize);
+
+/* Optional: pay the one-time costs of the host-pointer entry points now instead of inside the first sort --
+ * device buffers for arrays of up to max_n keys (and values when pairs != 0), the pinned staging ring, streams,
+ * the ranking self test of the device, and the first launch of every kernel of the default path.  The
+ * reference pays them inside sortByDevice on every call (cudaMalloc x 6 + 3 static buffers, Parallel7.cu:547-559,
+ * :203-218); here they are cached, so without this call only the first sort is slow. */
+int b200sort_warmup(uint64_t max_n, int pairs);
 
 /* Frees the cached device/pinned buffers of the host-pointer entry points (single- and
  * multi-GPU). */
@@ -90,14 +102,6 @@ int b200sort_mgpu_pairs_host(const uint32_t *h_keys_in, const uint32_t *h_vals_i
                              uint32_t *h_keys_out, uint32_t *h_vals_out, int nBits,
                              int blockSize, const int *devices, int num_devices);
 
-/* Figures of the last b200sort_mgpu_*_host call: out[0..6] = milliseconds of upload,
- * histogram, plan (host clock: splitters, receive buffers), partition kernel, wait for the
- * peers' partitions, local sort, download -- device-event times, each the maximum over the
- * devices, so they need not add up to the call's wall time; out[7] = partition shift,
- * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices, out[11] = 1 when
- * the splitters were key values from a sample (skewed keys; see b200sort_route) instead of bin
- * edges of the partition byte.
- * Returns the number of values written (<= capacity). */
 /* Host-side planning of the multi-GPU sorts, exported so that it can be exercised without a
  * GPU (tests compare it with the Python driver's planner, cuda/radixsort_b200/mgpu.py).
  * plan_owners: owner[b] = shard that receives bin b of the partition digit; cut j sits on the
@@ -113,6 +117,14 @@ int b200sort_plan_value_cuts(const uint32_t *sample_keys, const uint64_t *sample
                              const uint64_t *shard_offsets, int num_shards, uint64_t *values,
                              int *split_shard, uint64_t *split_pos);
 
+/* Figures of the last b200sort_mgpu_*_host call: out[0..6] = milliseconds of upload,
+ * histogram, plan (host clock: splitters, receive buffers), partition kernel, wait for the
+ * peers' partitions, local sort, download -- device-event times, each the maximum over the
+ * devices, so they need not add up to the call's wall time; out[7] = partition shift,
+ * out[8] = partition bits, out[9] = largest received range / (n / G), out[10] = devices, out[11] = 1 when
+ * the splitters were key values from a sample (skewed keys; see b200sort_route) instead of bin
+ * edges of the partition byte.
+ * Returns the number of values written (<= capacity). */
 enum { B200SORT_MGPU_STATS = 12 };
 int b200sort_mgpu_last_stats(double *out, int capacity);
 int b200sort_mgpu_shutdown(void);

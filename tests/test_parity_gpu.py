@@ -99,6 +99,45 @@ def test_host_entry_staging_chunk_boundaries(rs, oracle):
     assert np.array_equal(hk, k[idx]) and np.array_equal(hv, v[idx])
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_entry_overlapped_path(rs, oracle, pinned):
+    """From 2^24 keys on, the host-pointer entry (the sortByDevice replacement) uploads in chunks with the
+    top-4-bit histogram accumulated per chunk, splits on those bits (MSD) and sorts / downloads bucket by
+    bucket: same answer as the single-shot path and as the oracle -- uniform keys, keys that all fall into ONE
+    bucket, an empty top bucket, and stable pairs; pageable and pinned arrays."""
+    import torch
+    assert rs.get_param("host_overlap") == 1
+    n = (1 << 24) + 4099
+
+    def buf(a):
+        if not pinned:
+            return a
+        t = torch.from_numpy(a.view(np.int32)).pin_memory()
+        return t.numpy().view(np.uint32)
+
+    for kind, mask, orv in (("uniform", 0xFFFFFFFF, 0), ("uniform", 0x0FFFFFFF, 0x30000000), ("uniform", 0x7FFFFFFF, 0),
+                            ("zipf", 0xFFFFFFFF, 0)):
+        k = (oracle.generate(kind, n) & np.uint32(mask)) | np.uint32(orv)
+        want = oracle.sort_keys(k, 8)
+        hin, out = buf(k.copy()), buf(np.zeros_like(k))
+        rs.sortByDevice(hin, n, out, 8, 512)
+        assert np.array_equal(out, want), (kind, hex(mask))
+        assert np.array_equal(hin, k)                        # the input is not modified
+    rs.set_param("host_overlap", 0)
+    try:
+        out2 = np.zeros_like(k)
+        rs.sortByDevice(k, n, out2, 8, 512)                  # single-shot path
+    finally:
+        rs.set_param("host_overlap", 1)
+    assert np.array_equal(out2, want)
+    kk = oracle.generate("uniform", n) & np.uint32(0xF00000FF)   # 16 buckets x 256 values: long runs of equal keys
+    v = np.arange(n, dtype=np.uint32)
+    hk, hv = buf(np.zeros_like(kk)), buf(np.zeros_like(v))
+    rs.sort_pairs_by_device(buf(kk.copy()), buf(v.copy()), n, hk, hv, 8, 512)
+    rk, rv = oracle.sort_pairs(kk, v, 8)
+    assert np.array_equal(hk, rk) and np.array_equal(hv, rv)
+
+
 def test_keys_with_bit31_and_extremes(rs, oracle):
     k = oracle.generate("uniform", 100000)
     k[:5] = [0, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0xFFFFFFFF]
