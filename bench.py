@@ -657,6 +657,8 @@ def main():
     ap.add_argument("--no-narrow", action="store_true")
     ap.add_argument("--narrow-variant", type=int, default=None)
     ap.add_argument("--scan-variant", type=int, default=None)
+    ap.add_argument("--dst-bulk", type=int, default=None, choices=[0, 1],
+                    help="multi-GPU fused exchange: 1 = bulk-copy peer stores (default), 0 = 4-byte peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -668,6 +670,9 @@ def main():
     if args.narrow_variant is not None:
         import cuda.radixsort_b200 as rs
         rs.set_param("narrow_variant", args.narrow_variant)
+    if args.dst_bulk is not None:
+        import cuda.radixsort_b200 as rs
+        rs.set_param("dst_bulk", args.dst_bulk)
     if args.scan_variant is not None:
         import cuda.radixsort_b200 as rs
         rs.set_param("scan_variant", args.scan_variant)

@@ -36,6 +36,7 @@ struct Params {
     std::atomic<int> hist_ctas_per_sm{2};
     std::atomic<int> narrow_variant{-1}; // digit passes of <= 3 bits: -1 = kBallotVariant
     std::atomic<int> safe_rank{0};       // 1 = only kernels whose ranking follows from the PTX memory model
+    std::atomic<int> dst_bulk{1};        // digit pass with per-bin destinations, keys only: bulk-copy write-out
     std::atomic<int> host_overlap{1};    // host-pointer path: chunked upload + MSD split + per-bucket download
     std::atomic<int> scan_variant{8};    // tile geometry of b200sort_exclusive_scan (scan.cuh: kScanGeom)
 } g_params;
@@ -750,6 +751,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.host_overlap = value;
         return 0;
     }
+    if (!strcmp(name, "dst_bulk")) {
+        if (value != 0 && value != 1) return B200SORT_EINVAL;
+        g_params.dst_bulk = value;
+        return 0;
+    }
     if (!strcmp(name, "scan_variant")) {
         if (value < 0 || value >= kScanNumVariants) return B200SORT_EINVAL;
         g_params.scan_variant = value;
@@ -768,6 +774,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
     if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
     if (!strcmp(name, "host_overlap")) return g_params.host_overlap;
+    if (!strcmp(name, "dst_bulk")) return g_params.dst_bulk;
     if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
     if (!strcmp(name, "effective_variant")) return check_device() ? std::max<int>(g_params.variant.load(), 0) : effective_variant(8);
     if (!strcmp(name, "atomic_rank_ok")) return check_device() ? -1 : run_selftest();
@@ -901,6 +908,9 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     cudaStream_t s = (cudaStream_t)stream;
 
     int variant = effective_variant(bits, pairs);
+    // keys with per-bin destinations (the fused partition + exchange): the column-sweep kernel writes every
+    // (tile, bin) run with one shared->global bulk copy (UBLKCP) instead of 4-byte stores
+    if (dst && !pairs && g_params.dst_bulk) variant = kColVariant;
     if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant && variant != kColVariant)
         variant = variant_mode(variant) == 1 ? 1 : 0;
     if (variant_mode(variant) == 1 && (g_params.safe_rank || !run_selftest())) variant = kColVariant;

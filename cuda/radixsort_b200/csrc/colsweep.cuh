@@ -88,8 +88,12 @@ struct ColTraits {
     static constexpr int SCAN_ITEMS = ROWS * 4;   // (row, octet of columns) work items of the scan
     static constexpr int SCAN_ITERS = (SCAN_ITEMS + THREADS - 1) / THREADS;
     // word offsets inside dynamic shared memory
+    // keys-only kernels with per-bin destinations lay every bin out at the 16-byte phase of its destination
+    // (bulk-copy write-out): up to 6 words of padding per bin
+    static constexpr bool BULK = DST && !PAIRS;
+    static constexpr int PAD_WORDS = BULK ? (6 * B + 31) / 32 * 32 : 0;
     static constexpr int OFF_BUF = 0;                                   // keys [TILE] (+ values [TILE]); later the reorder buffer
-    static constexpr int OFF_TABLE = (PAIRS ? 2 : 1) * TILE;            // [ROWS][32], 128-byte aligned (TILE % 32 == 0)
+    static constexpr int OFF_TABLE = (PAIRS ? 2 : 1) * TILE + PAD_WORDS;  // [ROWS][32], 128-byte aligned (TILE % 32 == 0)
     static constexpr int OFF_BINSTART = OFF_TABLE + ROWS * 32;          // [B] first tile position of each bin
     static constexpr int OFF_GBASE = OFF_BINSTART + B;                  // [B] or [B] x 64 bit
     static constexpr int OFF_VBASE = OFF_GBASE + (DST ? 2 * B : B);     // [B] x 64 bit (DST pairs)
@@ -101,10 +105,48 @@ struct ColTraits {
     static_assert(W >= 1 && W <= 8, "digit width");
     static_assert(THREADS >= B, "one thread per bin");
     static_assert(COL % 8 == 4, "column stride must be an odd number of quads (WARPS odd, ITEMS % 8 == 4)");
-    static_assert(TILE * 4 < 65536, "byte positions must fit the 16-bit counters");
+    static_assert((TILE + PAD_WORDS) * 4 < 65536, "byte positions must fit the 16-bit counters");
     static_assert(WARPS <= 15, "one named barrier per hand-off");
     static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 };
+
+// shared -> global bulk copy (UBLKCP): bytes % 16 == 0, both addresses 16-byte aligned; completion is
+// tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(uint64_t gmem_dst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Exclusive prefix of bin `bin` over the tiles before `tile` (decoupled look-back, LB descriptors in flight).
+template <int B, int LB>
+__device__ __forceinline__ uint32_t look_back_one_bin(const uint32_t *desc, uint32_t tile, uint32_t bin, uint32_t st_not,
+                                                      uint32_t st_inc) {
+    uint32_t excl = 0;
+    const uint32_t *col = desc + bin;
+    int32_t t = (int32_t)tile - 1;
+    bool done = (tile == 0);
+    while (!done) {
+        uint32_t v[LB];
+#pragma unroll
+        for (int k = 0; k < LB; ++k) v[k] = (t - k >= 0) ? ld_relaxed_gpu(col + (size_t)(t - k) * B) : st_inc;
+        bool stop = false;
+#pragma unroll
+        for (int k = 0; k < LB; ++k) {
+            const uint32_t f = v[k] & kDescFlagMask;
+            if (!stop && f == st_not) stop = true;  // not published yet: poll again from here
+            if (!stop) {
+                excl += v[k] & kDescValueMask;
+                --t;
+                if (f == st_inc) { stop = true; done = true; }
+            }
+        }
+    }
+    return excl;
+}
 
 template <int W, int WARPS, int ITEMS, int MIN_CTAS, int LB, int GROUP, bool PAIRS, bool DST>
 __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(const PassArgs a) {
@@ -114,6 +156,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     constexpr int THREADS = TR::THREADS;
     constexpr int TILE = TR::TILE;
     constexpr int COL = TR::COL;
+    constexpr bool BULK = TR::BULK;
 
     extern __shared__ __align__(1024) uint32_t smem[];
     uint32_t *s_buf = smem + TR::OFF_BUF;
@@ -255,7 +298,19 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     if (tid < B) {
         const uint32_t count = ((s_rowtot[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu) >> 2;
         st_relaxed_gpu(a.desc + (size_t)tile * B + tid, (tile == 0 ? st_inc : st_agg) | count);
+        if (BULK) {
+            // The destination of this tile's run of every bin must be known BEFORE the keys are ranked: the
+            // run is laid out in shared memory at the 16-byte phase of its destination, so that its body is
+            // one shared->global bulk copy (to local or peer memory).  Predecessors publish their inclusive
+            // prefixes at this same early point, so the walk is short.
+            const uint32_t excl = look_back_one_bin<B, LB>(a.desc, tile, tid, st_not, st_inc);
+            if (tile != 0) st_relaxed_gpu(a.desc + (size_t)tile * B + tid, st_inc | (excl + count));
+            const uint32_t first = a.bin_base[tid] + excl;
+            if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[tid] = first + count;
+            reinterpret_cast<uint64_t *>(s_gbase)[tid] = a.bin_dst[tid] + 4ull * (uint64_t)first;  // address of the run
+        }
     }
+    if (BULK) __syncthreads();
     if (warp == 0) {
         uint32_t c[8];
 #pragma unroll
@@ -265,11 +320,25 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             c[2 * j] = w & 0xFFFFu;
             c[2 * j + 1] = w >> 16;
         }
+        uint32_t phase[8];  // BULK: byte offset of the run's destination inside its 16-byte line
+        uint32_t len[8];    // bytes the bin occupies in the reorder buffer (BULK: padded to whole 16-byte lines)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            phase[j] = 0;
+            len[j] = c[j];
+            if (BULK) {
+                const uint32_t bin = 8u * lane + j;
+                if (bin < (uint32_t)B && c[j] != 0u) {
+                    phase[j] = (uint32_t)reinterpret_cast<const uint64_t *>(s_gbase)[bin] & 15u;
+                    len[j] = (c[j] + phase[j] + 15u) & ~15u;
+                }
+            }
+        }
         uint32_t e[8];
         e[0] = 0;
 #pragma unroll
-        for (int j = 1; j < 8; ++j) e[j] = e[j - 1] + c[j - 1];
-        const uint32_t tot = e[7] + c[7];
+        for (int j = 1; j < 8; ++j) e[j] = e[j - 1] + len[j - 1];
+        const uint32_t tot = e[7] + len[7];
         uint32_t incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -279,7 +348,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         const uint32_t base = incl - tot;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (8u * lane + j < (uint32_t)B) s_binstart[8u * lane + j] = base + e[j];
+            if (8u * lane + j < (uint32_t)B) s_binstart[8u * lane + j] = base + e[j] + phase[j];
     }
     COL_STAMP(8);
     __syncthreads();
@@ -336,7 +405,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     constexpr int LB_WARPS = (WARPS - 1 < 4) ? WARPS - 1 : 4;
     constexpr int LBT = 32 * LB_WARPS;
     constexpr int NB = (B + LBT - 1) / LBT;
-    if (tid < (uint32_t)LBT) {
+    if (!BULK && tid < (uint32_t)LBT) {
         const uint32_t u = tid;
         uint32_t excl[NB];
         int32_t t[NB];
@@ -405,6 +474,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         }
     }
     COL_STAMP(12);
+    if (BULK) fence_proxy_async();  // generic-proxy scatter stores -> visible to the bulk-copy engine
     __syncthreads();
     COL_STAMP(16);
 
@@ -413,7 +483,27 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     uint32_t *const kout = a.keys_out;
     uint32_t *const vout = a.vals_out;
     constexpr int kWG = 6;  // loads in flight per thread
-    if (full) {
+    if (BULK) {
+        // One thread per bin: the run [S, S + bytes) of the reorder buffer goes to its destination as
+        // <= 3 head words, one bulk copy of whole 16-byte lines, <= 3 tail words.  The scatter stores were
+        // made visible to the async proxy by the fence every thread executed before the barrier above.
+        if (tid < B) {
+            uint32_t bytes = (s_rowtot[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
+            if (!full && tid == a.mask) bytes -= 4u * ((uint32_t)TILE - n_valid);  // the padding keys sit at the end of the top bin
+            if (bytes != 0u) {
+                const uint32_t src = sa_buf + s_binstart[tid];
+                const uint64_t dst = reinterpret_cast<const uint64_t *>(s_gbase)[tid];
+                const uint32_t head = min(bytes, (16u - ((uint32_t)dst & 15u)) & 15u);
+                const uint32_t body = (bytes - head) & ~15u;
+                const uint32_t tail = bytes - head - body;
+                if (body != 0u) bulk_s2g(dst + head, src + head, body);
+                for (uint32_t o = 0; o < head; o += 4u) *reinterpret_cast<uint32_t *>(dst + o) = sm_ld(src + o);
+                for (uint32_t o = head + body; o < head + body + tail; o += 4u)
+                    *reinterpret_cast<uint32_t *>(dst + o) = sm_ld(src + o);
+                if (body != 0u) bulk_commit_and_wait_read();  // the buffer must outlive the copy engine's reads
+            }
+        }
+    } else if (full) {
 #pragma unroll
         for (int k0 = 0; k0 < ITEMS; k0 += kWG) {
             uint32_t kk[kWG], vv[PAIRS ? kWG : 1], gb[kWG];

@@ -360,6 +360,39 @@ def test_digit_pass_with_per_bin_destinations(rs, oracle):
         assert int(kbufs[b][-1]) == 0       # nothing written past the bin
 
 
+@pytest.mark.parametrize("bulk", [1, 0])
+def test_digit_pass_destinations_at_every_alignment(rs, oracle, bulk):
+    """Keys with per-bin destinations are written by shared->global bulk copies (16-byte lines) with up to
+    three scalar head / tail words per (tile, bin) run: destinations at every 4-byte phase, bins of 1, 2, 3
+    and 8 bits (runs from thousands of keys down to a few), guard words around every bin."""
+    import torch
+    rs.set_param("dst_bulk", bulk)
+    try:
+        n = 3 * 10368 + 4001
+        for kind in ("uniform", "all_equal", "sorted"):
+            k = oracle.generate(kind, n)
+            for shift, bits in ((31, 1), (30, 2), (29, 3), (24, 8), (0, 8), (5, 3)):
+                nb = 1 << bits
+                d = (k >> shift) & (nb - 1)
+                counts = np.bincount(d, minlength=nb)
+                GUARD = 8
+                offs, pos = [], 0
+                for b in range(nb):
+                    pos += GUARD + (b % 4)                 # every 4-byte phase occurs
+                    offs.append(pos)
+                    pos += int(counts[b])
+                arena = torch.full((pos + GUARD,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+                table = torch.tensor([arena.data_ptr() + 4 * o for o in offs], dtype=torch.int64, device="cuda")
+                rs.digit_pass(to_dev(k), shift, bits, bin_dst=table)
+                got = to_host(arena)
+                expect = np.full(pos + GUARD, 0x5A5A5A5A, dtype=np.uint32)
+                for b in range(nb):
+                    expect[offs[b]: offs[b] + counts[b]] = k[d == b]
+                assert np.array_equal(got, expect), (kind, shift, bits, bulk)
+    finally:
+        rs.set_param("dst_bulk", 1)
+
+
 def test_exclusive_scan_matches_the_reference_scan_semantics(rs, oracle):
     """b200sort_exclusive_scan == the exclusive scan of the reference's scan() stage
     (SourceCode/Parallel7.cu:485-528; sequential form SourceCode/Baseline1.cu:39-42), mod 2^32."""
