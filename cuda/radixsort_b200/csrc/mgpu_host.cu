@@ -467,6 +467,9 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
         sh[d].out_first = running_out;
         running_out += tot;
     }
+    // The plan proper ends here (O(G * bins) host work).  Growing the cached receive / output / temp buffers
+    // below is cudaMalloc time, paid by the first call of a size only: it is not part of plan_ms.
+    const auto plan_t1 = std::chrono::steady_clock::now();
     for (int d = 0; d < G; ++d) {
         Shard &s = sh[d];
         CU(cudaSetDevice(s.dev));
@@ -490,8 +493,6 @@ int partition_and_exchange(std::vector<Shard> &sh, const uint32_t *hk_in, uint64
         if (by_value) t = std::max(t, b200sort_temp_bytes(s.count, part_bits, true));
         if (t > s.temp.bytes) RC(s.temp.ensure(align_up(t, 256)));
     }
-
-    const auto plan_t1 = std::chrono::steady_clock::now();
 
     // ---- partition fused with the exchange -------------------------------------------------------
     std::vector<uint64_t> src_base(G, 0);  // keys of lower source ranks already placed in each owner's range

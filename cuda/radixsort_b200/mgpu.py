@@ -98,7 +98,7 @@ def plan_exchange(counts_all: np.ndarray, rank: int, owner=None):
             narrow_bits = lg
     return {"owner": owner, "matrix": matrix, "send_counts": send_counts, "recv_counts": recv_counts,
             "recv_offsets": recv_offsets, "my_total": int(recv_counts.sum()),
-            "bin_recv_offset": bin_recv_offset, "totals": matrix.sum(axis=0),
+            "bin_recv_offset": bin_recv_offset, "totals": matrix.sum(axis=0), "shard_sizes": matrix.sum(axis=1),
             "src_base": src_base, "narrow_bits": narrow_bits}
 
 
@@ -267,17 +267,38 @@ class ShardedSorter:
             self._allocate(self.capacity)
 
     # -- buffers ------------------------------------------------------------------------------
+    def _agree(self, ok: bool) -> bool:
+        """True only if every rank of the group says ok (ranks must take the same exchange path)."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda" if self.on_gpu else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(flag.item()))
+
     def _allocate(self, capacity: int):
+        """capacity must be identical on every rank (symmetric buffers; callers derive it from gathered data)."""
         self.capacity = capacity
         if self.fused:
+            err = None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 self.recv = symm_mem.empty(capacity, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
-                self.symm = symm_mem.rendezvous(self.recv, self.group.group_name)
-                self.peer_ptrs = [int(p) for p in self.symm.buffer_ptrs]
-            except Exception as e:  # symmetric memory unavailable: NCCL exchange
+            except Exception as e:  # symmetric memory unavailable on this rank
+                err = repr(e)
+            # a rank that could not allocate must not leave its peers waiting in the rendezvous / barriers
+            if self._agree(err is None):
+                try:
+                    self.symm = symm_mem.rendezvous(self.recv, self.group.group_name)
+                    self.peer_ptrs = [int(p) for p in self.symm.buffer_ptrs]
+                except Exception as e:
+                    err = repr(e)
+                if not self._agree(err is None):
+                    err = err or "a peer could not rendezvous"
+            else:
+                err = err or "a peer could not allocate symmetric memory"
+            if err is not None:  # every rank falls back to the NCCL exchange together
                 self.fused = False
-                self.fused_error = repr(e)
+                self.fused_error = err
+                self.symm = None
+                self.peer_ptrs = None
         if not self.fused:
             self.recv = self.ops.empty(capacity)
         self.out = self.ops.empty(capacity)
@@ -394,7 +415,9 @@ class ShardedSorter:
         if self.recv is None or need > self.capacity:
             if self.fused and self.recv is not None:
                 raise RuntimeError(f"receive capacity {self.capacity} < {need}: construct ShardedSorter with a larger per_rank_capacity")
-            self._allocate(max(need, int(n_local * 1.05) + 1024))
+            # sized from values every rank holds (the gathered counts), never from the local shard alone
+            largest_shard = int(plan["shard_sizes"].max()) if "shard_sizes" in plan else n_local
+            self._allocate(max(need, int(largest_shard * 1.05) + 1024))
         if vals is not None:
             self._allocate_values()
 
