@@ -25,6 +25,8 @@ INCLUDE_DIR = os.path.normpath(os.path.join(PKG_DIR, "..", "..", "include"))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-pthread", "-I", INCLUDE_DIR]
+if os.environ.get("B200_TUNING"):
+    NVCC_FLAGS.append("-DB200_TUNING")  # every kernel geometry of csrc/launch.h (tools/sweep.py, the variant tests)
 if os.environ.get("B200_COL_NOTMA"):
     NVCC_FLAGS.append("-DB200_COL_NOTMA")  # experiment: tile loaded with LDG + STS instead of the bulk-copy engine
 if os.environ.get("B200_COL_DEBUG"):
@@ -56,7 +58,13 @@ def _run(cmd: list[str], verbose: bool) -> None:
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     """Compile (if stale) and return the path of libb200sort.so."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _sources_mtime():
+    flags_file = os.path.join(BUILD_DIR, "flags.txt")
+    flags_now = " ".join(NVCC_FLAGS)
+    try:
+        same_flags = open(flags_file).read() == flags_now
+    except OSError:
+        same_flags = False
+    if not force and same_flags and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _sources_mtime():
         return LIB_PATH
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = _nvcc()
@@ -77,6 +85,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
         list(pool.map(lambda c: _run(c, verbose or ptxas_info), jobs))
     _run([nvcc, *ARCH, "-shared", "-Xcompiler", "-pthread", "-o", LIB_PATH, *objs], verbose)
+    with open(flags_file, "w") as f:
+        f.write(flags_now)
     build_cli(verbose)
     return LIB_PATH
 

@@ -204,7 +204,7 @@ int effective_variant(int width, bool pairs = false) {
     if (v < 0)
         v = (width == 8) ? (pairs ? kAutoVariantW8Pairs : kAutoVariantW8)
                          : (width <= 3 ? (narrow >= 0 ? narrow : kBallotVariant) : 1);
-    if (!variant_available(width, v)) v = 0;
+    if (!variant_available(width, v)) v = fallback_variant(width);
     // Atomic-rank kernels need same-address shared atomics of one warp instruction to be applied in lane
     // order (not promised by PTX): they run only on a device that passed the self test, and never when
     // the caller asked for spec-safe ranking -- the column-sweep kernel (lane-private counters, ordered
@@ -771,6 +771,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "hist_ctas_per_sm")) return g_params.hist_ctas_per_sm;
     if (!strcmp(name, "mgpu_balance_permille")) return g_mgpu_balance_permille.load();
     if (!strcmp(name, "num_variants")) return kNumVariants;
+    if (!strcmp(name, "tuning_build")) return kTuningBuild ? 1 : 0;
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
     if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
     if (!strcmp(name, "host_overlap")) return g_params.host_overlap;
@@ -911,8 +912,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
     // keys with per-bin destinations (the fused partition + exchange): the column-sweep kernel writes every
     // (tile, bin) run with one shared->global bulk copy (UBLKCP) instead of 4-byte stores
     if (dst && !pairs && g_params.dst_bulk) variant = kColVariant;
-    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant && variant != kColVariant)
-        variant = variant_mode(variant) == 1 ? 1 : 0;
+    if (dst && !variant_has_dst(bits, variant)) variant = fallback_variant(bits);
     if (variant_mode(variant) == 1 && (g_params.safe_rank || !run_selftest())) variant = kColVariant;
     const int tile = tile_keys(variant, pairs);
     const Layout L = make_layout(n, 1, bits, pairs, false, tile, g_params.portion_tiles);

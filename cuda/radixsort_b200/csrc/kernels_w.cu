@@ -81,13 +81,17 @@ cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
 
 template <int V>
 cudaError_t launch_modes(bool pairs, bool dst, const PassArgs &a, cudaStream_t s) {
-    if (!pairs && !dst) return launch_variant<V, false, false>(a, s);
-    if (pairs && !dst) return launch_variant<V, true, false>(a, s);
-    if constexpr (V <= 1 || V == kBallotVariant || V == kBallotSmallVariant || V == kColVariant) {
-        if (!pairs && dst) return launch_variant<V, false, true>(a, s);
-        return launch_variant<V, true, true>(a, s);
+    if constexpr (!variant_compiled(W, V)) {
+        return cudaErrorInvalidValue;
+    } else {
+        if (!pairs && !dst) return launch_variant<V, false, false>(a, s);
+        if (pairs && !dst) return launch_variant<V, true, false>(a, s);
+        if constexpr (variant_has_dst(W, V)) {
+            if (!pairs && dst) return launch_variant<V, false, true>(a, s);
+            return launch_variant<V, true, true>(a, s);
+        }
+        return cudaErrorInvalidValue;
     }
-    return cudaErrorInvalidValue;
 }
 
 template <int P_CT>
@@ -118,7 +122,8 @@ cudaError_t B200_CAT(launch_hist_w, B200_W)(bool uniform, const HistArgs &a, int
 
 cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, const PassArgs &a,
                                             cudaStream_t s) {
-    if (dst && variant > 1 && variant != kBallotVariant && variant != kBallotSmallVariant && variant != kColVariant) variant = 0;
+    if (!variant_compiled(W, variant)) variant = fallback_variant(W);
+    if (dst && !variant_has_dst(W, variant)) variant = fallback_variant(W);
     switch (variant) {
     case 0: return launch_modes<0>(pairs, dst, a, s);
     case 1: return launch_modes<1>(pairs, dst, a, s);

@@ -248,6 +248,11 @@ def test_kernel_variants(rs, oracle, variant):
     rs.set_param("variant", variant)
     try:
         assert variant < rs.get_param("num_variants")
+        if rs.get_param("effective_variant") != variant:
+            # the product library carries only the kernels its automatic choice can select; the other
+            # geometries need the tuning build (B200_TUNING=1 python -m cuda.radixsort_b200.build --force)
+            assert rs.get_param("tuning_build") == 0 or rs.get_param("atomic_rank_ok") != 1
+            pytest.skip("variant not in this build")
         n = (1 << 20) + 12345
         k = oracle.generate("uniform", n)
         assert np.array_equal(dev_sort(rs, k, 8), oracle.sort_keys(k, 8))

@@ -48,6 +48,8 @@ def main():
     for v in variants:
         rs.set_param("variant", v)
         eff = rs.get_param("effective_variant")
+        if eff != v and not rs.get_param("tuning_build"):
+            continue  # not in the product build: B200_TUNING=1 python -m cuda.radixsort_b200.build --force
 
         def step():
             if pairs:
