@@ -103,7 +103,6 @@ struct ColTraits {
     static constexpr int SMEM_WORDS = OFF_BAR + 2;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
     static_assert(W >= 1 && W <= 8, "digit width");
-    static_assert(THREADS >= B, "one thread per bin");
     static_assert(COL % 8 == 4, "column stride must be an odd number of quads (WARPS odd, ITEMS % 8 == 4)");
     static_assert((TILE + PAD_WORDS) * 4 < 65536, "byte positions must fit the 16-bit counters");
     static_assert(WARPS <= 15, "one named barrier per hand-off");
@@ -295,19 +294,19 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t st_not = ((2u * a.parity) & 3u) << 30;
     const uint32_t st_agg = ((2u * a.parity + 1u) & 3u) << 30;
     const uint32_t st_inc = ((2u * a.parity + 2u) & 3u) << 30;
-    if (tid < B) {
-        const uint32_t count = ((s_rowtot[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu) >> 2;
-        st_relaxed_gpu(a.desc + (size_t)tile * B + tid, (tile == 0 ? st_inc : st_agg) | count);
+    for (uint32_t bin = tid; bin < (uint32_t)B; bin += THREADS) {
+        const uint32_t count = ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu) >> 2;
+        st_relaxed_gpu(a.desc + (size_t)tile * B + bin, (tile == 0 ? st_inc : st_agg) | count);
         if (BULK) {
             // The destination of this tile's run of every bin must be known BEFORE the keys are ranked: the
             // run is laid out in shared memory at the 16-byte phase of its destination, so that its body is
             // one shared->global bulk copy (to local or peer memory).  Predecessors publish their inclusive
             // prefixes at this same early point, so the walk is short.
-            const uint32_t excl = look_back_one_bin<B, LB>(a.desc, tile, tid, st_not, st_inc);
-            if (tile != 0) st_relaxed_gpu(a.desc + (size_t)tile * B + tid, st_inc | (excl + count));
-            const uint32_t first = a.bin_base[tid] + excl;
-            if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[tid] = first + count;
-            reinterpret_cast<uint64_t *>(s_gbase)[tid] = a.bin_dst[tid] + 4ull * (uint64_t)first;  // address of the run
+            const uint32_t excl = look_back_one_bin<B, LB>(a.desc, tile, bin, st_not, st_inc);
+            if (tile != 0) st_relaxed_gpu(a.desc + (size_t)tile * B + bin, st_inc | (excl + count));
+            const uint32_t first = a.bin_base[bin] + excl;
+            if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[bin] = first + count;
+            reinterpret_cast<uint64_t *>(s_gbase)[bin] = a.bin_dst[bin] + 4ull * (uint64_t)first;  // address of the run
         }
     }
     if (BULK) __syncthreads();
@@ -487,12 +486,12 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         // One thread per bin: the run [S, S + bytes) of the reorder buffer goes to its destination as
         // <= 3 head words, one bulk copy of whole 16-byte lines, <= 3 tail words.  The scatter stores were
         // made visible to the async proxy by the fence every thread executed before the barrier above.
-        if (tid < B) {
-            uint32_t bytes = (s_rowtot[tid >> 1] >> ((tid & 1u) * 16u)) & 0xFFFFu;
-            if (!full && tid == a.mask) bytes -= 4u * ((uint32_t)TILE - n_valid);  // the padding keys sit at the end of the top bin
+        for (uint32_t bin = tid; bin < (uint32_t)B; bin += THREADS) {
+            uint32_t bytes = (s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu;
+            if (!full && bin == a.mask) bytes -= 4u * ((uint32_t)TILE - n_valid);  // the padding keys sit at the end of the top bin
             if (bytes != 0u) {
-                const uint32_t src = sa_buf + s_binstart[tid];
-                const uint64_t dst = reinterpret_cast<const uint64_t *>(s_gbase)[tid];
+                const uint32_t src = sa_buf + s_binstart[bin];
+                const uint64_t dst = reinterpret_cast<const uint64_t *>(s_gbase)[bin];
                 const uint32_t head = min(bytes, (16u - ((uint32_t)dst & 15u)) & 15u);
                 const uint32_t body = (bytes - head) & ~15u;
                 const uint32_t tail = bytes - head - body;

@@ -170,6 +170,12 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 41: return launch_modes<41>(pairs, dst, a, s);
     case 42: return launch_modes<42>(pairs, dst, a, s);
     case 43: return launch_modes<43>(pairs, dst, a, s);
+    case 44: return launch_modes<44>(pairs, dst, a, s);
+    case 45: return launch_modes<45>(pairs, dst, a, s);
+    case 46: return launch_modes<46>(pairs, dst, a, s);
+    case 47: return launch_modes<47>(pairs, dst, a, s);
+    case 48: return launch_modes<48>(pairs, dst, a, s);
+    case 49: return launch_modes<49>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

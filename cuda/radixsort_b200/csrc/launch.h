@@ -18,7 +18,7 @@ struct PassVariant {
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA
 };
-constexpr int kNumVariants = 44;
+constexpr int kNumVariants = 50;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -65,6 +65,12 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {288, 28, 20, 3, 3, 28, 4, 0},  // 41 28 keys, a whole turn in flight
     {288, 36, 20, 3, 3, 36, 4, 0},  // 42 = 36, a whole turn in flight
     {288, 28, 12, 4, 3, 14, 4, 0},  // 43 four CTAs per SM
+    {160, 52, 28, 4, 3, 13, 4, 0},  // 44 five warps (shorter chain), four CTAs per SM
+    {160, 36, 20, 5, 3, 12, 4, 0},  // 45 five warps, five CTAs per SM
+    {224, 44, 20, 3, 3, 11, 4, 0},  // 46 seven warps, three CTAs per SM
+    {224, 36, 20, 4, 3, 12, 4, 0},  // 47 seven warps, four CTAs per SM
+    {160, 68, 36, 3, 3, 17, 4, 0},  // 48 five warps x 68 keys, three CTAs per SM
+    {96, 84, 44, 5, 3, 14, 4, 0},   // 49 three warps x 84 keys, five CTAs per SM
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) onesweep_pass_kernel(const 
 // that every lane got back the sum of the addends of all earlier instructions plus those of the LOWER
 // lanes of the same instruction with the same digit; the odd warps meanwhile hammer the banks of the
 // neighbouring table with reductions, stores and loads (the count, reorder and write-out traffic of
-// other warps).  mismatches[0] counts violations.  ~0.3 ms, once per device and process.
+// other warps).  mismatches[0] counts violations.  ~3 ms, once per device and process.
 template <int UNUSED>  // template only so the header can be included in several translation units
 __global__ void __launch_bounds__(256, 3) atomic_order_selftest(uint32_t *mismatches, int rounds, uint32_t seed) {
     __shared__ __align__(1024) uint32_t table[8][256];

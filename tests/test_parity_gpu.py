@@ -243,7 +243,7 @@ def test_multi_launch_portions(rs, oracle):
         rs.set_param("portion_tiles", 0)
 
 
-@pytest.mark.parametrize("variant", list(range(44)))
+@pytest.mark.parametrize("variant", list(range(50)))
 def test_kernel_variants(rs, oracle, variant):
     rs.set_param("variant", variant)
     try:
