@@ -670,6 +670,29 @@ void set_error_message(const char *message) { g_last_error = message ? message :
 
 }  // namespace b200sort
 
+namespace b200sort {
+namespace {
+template <int THREADS, int VECS>
+cudaError_t launch_scan_persistent(const uint32_t *d_in, uint32_t *d_out, uint64_t n, uint64_t *desc, uint32_t tiles,
+                                   cudaStream_t s) {
+    auto kernel = exclusive_scan_persistent_kernel<THREADS, VECS>;
+    static std::atomic<int> resident[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &slot = *reinterpret_cast<int *>(&resident[dev & (kMaxDevices - 1)]);
+    if (slot == 0) {  // every CTA must be resident: tiles spin on tiles held by other CTAs of the launch
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0);
+        if (e != cudaSuccess) return e;
+        slot = std::max(1, per_sm) * std::max(1, num_sms());
+    }
+    kernel<<<std::min<unsigned>(tiles, (unsigned)slot), THREADS, 0, s>>>(d_in, d_out, n, desc, tiles);
+    return cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace b200sort
+
 using namespace b200sort;
 
 // =====================================================================================================
@@ -966,7 +989,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
 }
 
 size_t b200sort_scan_temp_bytes(uint64_t n) {
-    return align_up(((n + kScanMinTile - 1) / kScanMinTile) * sizeof(uint64_t), 256) + 256;
+    return align_up(((n + kScanMinTile - 1) / kScanMinTile + 1) * sizeof(uint64_t), 256) + 256;
 }
 
 int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp, size_t temp_bytes,
@@ -983,7 +1006,7 @@ int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, v
     int rc = check_device();
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaMemsetAsync(d_temp, 0, tiles * sizeof(uint64_t), s));
+    CU(cudaMemsetAsync(d_temp, 0, (tiles + 1) * sizeof(uint64_t), s));  // descriptors + the ticket of the persistent form
     g_launches.fetch_add(1, std::memory_order_relaxed);
     uint64_t *desc = static_cast<uint64_t *>(d_temp);
     switch (sv) {
@@ -995,7 +1018,11 @@ int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, v
     case 5: exclusive_scan_kernel<128, 8><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
     case 6: exclusive_scan_kernel<256, 8><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
     case 7: exclusive_scan_kernel<256, 16><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
-    default: exclusive_scan_kernel<128, 16><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
+    case 8: exclusive_scan_kernel<128, 16><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
+    case 9: CU((launch_scan_persistent<1024, 4>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
+    case 10: CU((launch_scan_persistent<512, 8>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
+    case 11: CU((launch_scan_persistent<512, 4>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
+    default: CU((launch_scan_persistent<256, 8>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
     }
     CU(cudaGetLastError());
     return 0;

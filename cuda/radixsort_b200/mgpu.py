@@ -82,11 +82,11 @@ def plan_exchange(counts_all: np.ndarray, rank: int, owner=None):
     if rank > 0:
         src_base = matrix[:rank].sum(axis=0)
     bin_recv_offset = np.zeros(bins, dtype=np.int64)
-    running = src_base.copy()
-    for b in range(bins):
-        d = owner[b]
-        bin_recv_offset[b] = running[d]
-        running[d] += counts_all[rank, b]
+    mine = counts_all[rank]
+    for d in range(world):              # vectorised per owner (the planner runs while the GPU waits)
+        sel = owner == d
+        c = mine[sel]
+        bin_recv_offset[sel] = src_base[d] + np.cumsum(c) - c
     # Splitters that coincide with the top log2(world) bits (uniform keys on 2/4/8 ranks): the
     # partition can then run as a log2(world)-bit digit pass -- 2..8 bins instead of 256, i.e.
     # runs of thousands of keys per (tile, destination), which is what NVLink stores want.
