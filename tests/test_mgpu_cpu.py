@@ -57,6 +57,29 @@ def test_plan_exchange_is_consistent_across_ranks():
         assert [x[2] for x in spans if x[1]] == sorted(x[2] for x in spans if x[1])   # grouped by source rank
 
 
+def test_plan_exchange_offsets_match_a_sequential_walk():
+    """bin_recv_offset (vectorised per owner) == the obvious walk over the bins in order, for random count
+    matrices and for owners that leave some ranks without bins."""
+    rng = np.random.default_rng(11)
+    for world in (2, 3, 4, 8):
+        for trial in range(6):
+            bins = 256
+            counts = rng.integers(0, 1000, size=(world, bins)).astype(np.int64)
+            if trial % 2:                                   # heavy skew: most bins empty, one rank starves
+                counts[:, rng.integers(0, bins, 200)] = 0
+                counts[:, 7] += 500000
+            for rank in range(world):
+                plan = mgpu.plan_exchange(counts, rank)
+                owner, matrix = plan["owner"], plan["matrix"]
+                running = matrix[:rank].sum(axis=0).astype(np.int64) if rank else np.zeros(world, np.int64)
+                expect = np.zeros(bins, np.int64)
+                for b in range(bins):
+                    expect[b] = running[owner[b]]
+                    running[owner[b]] += counts[rank, b]
+                assert np.array_equal(plan["bin_recv_offset"], expect), (world, trial, rank)
+                assert np.array_equal(plan["shard_sizes"], counts.sum(axis=1))
+
+
 def test_narrow_partition_detection():
     uniform = np.full((4, 256), 100)
     assert mgpu.plan_exchange(uniform, 0)["narrow_bits"] == 2
