@@ -78,10 +78,10 @@ __device__ long long g_col_dbg[16 * 20];
 #define COL_STAMP(k) do { } while (0)
 #endif
 
-template <int W, int WARPS, int ITEMS, bool PAIRS, bool DST>
+template <int W, int WARPS, int ITEMS, bool PAIRS, bool DST, bool WIDE = false, bool DUAL = false>
 struct ColTraits {
     static constexpr int B = 1 << W;
-    static constexpr int ROWS = B / 2;            // two bins per 32-bit counter word
+    static constexpr int ROWS = WIDE ? B : B / 2;  // packed: two bins per 32-bit counter word; WIDE: one
     static constexpr int THREADS = 32 * WARPS;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int COL = WARPS * ITEMS;     // keys per column (= per lane)
@@ -90,7 +90,7 @@ struct ColTraits {
     // word offsets inside dynamic shared memory
     // keys-only kernels with per-bin destinations lay every bin out at the 16-byte phase of its destination
     // (bulk-copy write-out): up to 6 words of padding per bin
-    static constexpr bool BULK = DST && !PAIRS;
+    static constexpr bool BULK = DST && !PAIRS && !WIDE;
     static constexpr int PAD_WORDS = BULK ? (6 * B + 31) / 32 * 32 : 0;
     static constexpr int OFF_BUF = 0;                                   // keys [TILE] (+ values [TILE]); later the reorder buffer
     static constexpr int OFF_TABLE = (PAIRS ? 2 : 1) * TILE + PAD_WORDS;  // [ROWS][32], 128-byte aligned (TILE % 32 == 0)
@@ -103,8 +103,14 @@ struct ColTraits {
     static constexpr int SMEM_WORDS = OFF_BAR + 2;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_WORDS * 4;
     static_assert(W >= 1 && W <= 8, "digit width");
-    static_assert(COL % 8 == 4, "column stride must be an odd number of quads (WARPS odd, ITEMS % 8 == 4)");
-    static_assert((TILE + PAD_WORDS) * 4 < 65536, "byte positions must fit the 16-bit counters");
+    // DUAL: the warps form two groups (A = warps [0, WA), B = the rest), each with its own half of the tile
+    // and its own 16-bit half of every counter word; both group sizes odd
+    static constexpr int WA = !DUAL ? WARPS : ((WARPS / 2) % 2 == 1 ? WARPS / 2 : WARPS / 2 + 1);
+    static constexpr int COL_A = WA * ITEMS;
+    static constexpr int COL_B = (WARPS - WA) * ITEMS;
+    static_assert(DUAL ? (COL_A % 8 == 4 && COL_B % 8 == 4) : (COL % 8 == 4),
+                  "column stride must be an odd number of quads (odd warp count per group, ITEMS % 8 == 4)");
+    static_assert(WIDE || (TILE + PAD_WORDS) * 4 < 65536, "byte positions must fit the 16-bit counters");  // the DUAL kernel checks its own
     static_assert(WARPS <= 15, "one named barrier per hand-off");
     static_assert((OFF_BAR % 2) == 0, "mbarrier alignment");
 };
@@ -147,14 +153,13 @@ __device__ __forceinline__ uint32_t look_back_one_bin(const uint32_t *desc, uint
     return excl;
 }
 
-template <int W, int WARPS, int ITEMS, int MIN_CTAS, int LB, int GROUP, bool PAIRS, bool DST>
+template <int W, int WARPS, int ITEMS, int MIN_CTAS, int LB, int GROUP, bool PAIRS, bool DST, bool WIDE = false, bool DUAL = false, bool AGENT = false, bool LBV4 = false>
 __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(const PassArgs a) {
-    using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST>;
+    using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST, WIDE, DUAL>;
     constexpr int B = TR::B;
     constexpr int ROWS = TR::ROWS;
     constexpr int THREADS = TR::THREADS;
     constexpr int TILE = TR::TILE;
-    constexpr int COL = TR::COL;
     constexpr bool BULK = TR::BULK;
 
     extern __shared__ __align__(1024) uint32_t smem[];
@@ -170,7 +175,57 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t sa_table = smem_u32(smem + TR::OFF_TABLE);
     const uint32_t sa_tlane = sa_table + lane * 4u;  // this lane's column of the counter table
 
-    const uint32_t tile = blockIdx.x;
+    // AGENT: CTA 0 of the grid owns no tile.  It walks the descriptor rows in tile order, one thread per bin, and
+    // replaces every AGGREGATE by the exclusive prefix of the tiles before it (flag INCLUSIVE), so a tile learns its
+    // offsets by polling its OWN row: ~2 L2 round trips after its counts were published, where the decoupled
+    // look-back of every tile walks ~20 predecessors in 5-7 dependent round trips (measured: it ends 3 k cycles
+    // after the ranking).  One row per ~35 cycles (AGENT_WIN rows per round trip); the tiles arrive every ~55.
+    if constexpr (AGENT) if (blockIdx.x == 0) {
+        constexpr int AGENT_WIN = 40;
+        constexpr int ANB = (B + THREADS - 1) / THREADS;
+        static_assert(ANB <= 2, "agent: at most two bins per thread");
+        const uint32_t a_not = ((2u * a.parity) & 3u) << 30, a_agg = ((2u * a.parity + 1u) & 3u) << 30;
+        const uint32_t a_inc = ((2u * a.parity + 2u) & 3u) << 30;
+        uint32_t sum[ANB], at[ANB];
+        bool fin[ANB];
+        bool all = true;
+#pragma unroll
+        for (int j = 0; j < ANB; ++j) {
+            sum[j] = 0;
+            at[j] = 0;
+            fin[j] = (tid + j * THREADS >= (uint32_t)B) || a.num_tiles == 0;
+            all = all && fin[j];
+        }
+        while (!all) {
+            all = true;
+#pragma unroll
+            for (int j = 0; j < ANB; ++j) {
+                if (fin[j]) continue;
+                uint32_t *col = a.desc + (tid + j * THREADS);
+                uint32_t v[AGENT_WIN];
+#pragma unroll
+                for (int k = 0; k < AGENT_WIN; ++k)
+                    v[k] = (at[j] + k < a.num_tiles) ? ld_relaxed_gpu(col + (size_t)(at[j] + k) * B) : a_not;
+                bool stop = false;
+                uint32_t adv = 0;
+#pragma unroll
+                for (int k = 0; k < AGENT_WIN; ++k) {
+                    if (!stop && (v[k] & kDescFlagMask) == a_agg) {
+                        st_relaxed_gpu(col + (size_t)(at[j] + k) * B, a_inc | sum[j]);
+                        sum[j] += v[k] & kDescValueMask;
+                        ++adv;
+                    } else {
+                        stop = true;
+                    }
+                }
+                at[j] += adv;
+                fin[j] = at[j] >= a.num_tiles;
+                all = all && fin[j];
+            }
+        }
+        return;
+    }
+    const uint32_t tile = AGENT ? blockIdx.x - 1u : blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
@@ -184,7 +239,29 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t m3 = (a.mask >> 1) << 3;
     const uint32_t rot_w = (a.shift + 30u) & 31u;           // write-out: d * 4 at bits 2..9
     const uint32_t mask4 = a.mask << 2;
+    // WIDE: one 32-bit counter per (bin, lane) -- row = digit, constant addend, no half to select.  The keys
+    // stay ROTATED (digit * 4 at bits 2..9) in the registers and in the reorder buffer from the load to the
+    // write-out, so a table address is two instructions ((r & mask4) << 5) + column) and the counters hold
+    // absolute shared-memory addresses: the turn of a warp in the chain is 3 instructions per key.
+    const uint32_t mask4_rank = launder(mask4, a.parity >> 8);
+    // DUAL (with WIDE): a warp's ranking atomics complete one after the other (16.5 cycles each on B200,
+    // tools/gpu_probe3.cu) while those of different warps overlap, so the tile is split into two halves that are
+    // ranked at the same time.  Group A (warps [0, WA)) owns tile positions [0, 32 * COL_A) as 32 columns, group
+    // B the rest; the word of (bin, lane) holds A's 16-bit counter in its low half and B's in its high half, so
+    // the scan is the packed scan of two independent column sets, a bin's keys are A's (column order) followed
+    // by B's = index order, and each group runs its own chain of turns.  The addend is a per-warp constant, the
+    // half of the returned word a per-warp byte selector.
+    static_assert(!DUAL || (WIDE && TR::TILE * 4 < 65536), "DUAL: 16-bit byte positions");
+    constexpr uint32_t WA = TR::WA;
+    const bool group_b = DUAL && warp >= WA;
+    const uint32_t gadd = group_b ? (4u << 16) : 4u;
+    const uint32_t gsel = group_b ? 0x4432u : 0x4410u;
+    auto tile_bytes = [&](uint32_t bin) -> uint32_t {  // bytes of bin `bin` in this tile (4 per key)
+        return DUAL ? (s_rowtot[bin] & 0xFFFFu) + (s_rowtot[bin] >> 16)
+                    : WIDE ? s_rowtot[bin] : ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu);
+    };
 
+    static_assert(!AGENT || !TR::BULK, "the agent serves the look-back of the non-bulk write-out");
     COL_STAMP(0);
     // ---- 0. tile -> shared memory --------------------------------------------------------------
 #ifdef B200_COL_NOTMA
@@ -224,7 +301,9 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     uint32_t key[ITEMS];
     uint32_t val[PAIRS ? ITEMS : 1];
     {
-        const uint32_t src = sa_buf + (lane * (uint32_t)COL + warp * (uint32_t)ITEMS) * 4u;
+        const uint32_t first = !group_b ? lane * (uint32_t)TR::COL_A + warp * (uint32_t)ITEMS
+                                        : 32u * TR::COL_A + lane * (uint32_t)TR::COL_B + (warp - WA) * (uint32_t)ITEMS;
+        const uint32_t src = sa_buf + first * 4u;
 #pragma unroll
         for (int q = 0; q < ITEMS / 4; ++q) {
             const uint4 v = sm_ld4(src + 16u * q);
@@ -237,14 +316,22 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
                 val[4 * q] = v.x; val[4 * q + 1] = v.y; val[4 * q + 2] = v.z; val[4 * q + 3] = v.w;
             }
         }
+        if (WIDE) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = __funnelshift_r(key[i], key[i], rot);
+        }
     }
 
     COL_STAMP(3);
     // ---- 2. count --------------------------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const uint32_t r = __funnelshift_r(key[i], key[i], rot);
-        sm_red((r & m3) * 16u + sa_tlane, (r & 4u) * 0xFFFFu + 4u);
+        if (WIDE) {
+            sm_red(((key[i] & mask4) << 5) + sa_tlane, gadd);
+        } else {
+            const uint32_t r = __funnelshift_r(key[i], key[i], rot);
+            sm_red((r & m3) * 16u + sa_tlane, (r & 4u) * 0xFFFFu + 4u);
+        }
     }
     COL_STAMP(4);
     __syncthreads();  // counts complete; every thread holds its keys, so the buffer may be overwritten
@@ -269,15 +356,18 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             lo = par ? qb : qa;
             hi = par ? qa : qb;
         }
-        ex[k][0] = 0;
-        ex[k][1] = lo.x;
-        ex[k][2] = ex[k][1] + lo.y;
-        ex[k][3] = ex[k][2] + lo.z;
-        ex[k][4] = ex[k][3] + lo.w;
-        ex[k][5] = ex[k][4] + hi.x;
-        ex[k][6] = ex[k][5] + hi.y;
-        ex[k][7] = ex[k][6] + hi.z;
-        const uint32_t tot = ex[k][7] + hi.w;
+        uint32_t tot;
+        {
+            ex[k][0] = 0;
+            ex[k][1] = lo.x;
+            ex[k][2] = ex[k][1] + lo.y;
+            ex[k][3] = ex[k][2] + lo.z;
+            ex[k][4] = ex[k][3] + lo.w;
+            ex[k][5] = ex[k][4] + hi.x;
+            ex[k][6] = ex[k][5] + hi.y;
+            ex[k][7] = ex[k][6] + hi.z;
+            tot = ex[k][7] + hi.w;
+        }
         uint32_t incl = tot;
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, 1, 4);
         if (g >= 1u) incl += t;
@@ -295,8 +385,8 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t st_agg = ((2u * a.parity + 1u) & 3u) << 30;
     const uint32_t st_inc = ((2u * a.parity + 2u) & 3u) << 30;
     for (uint32_t bin = tid; bin < (uint32_t)B; bin += THREADS) {
-        const uint32_t count = ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu) >> 2;
-        st_relaxed_gpu(a.desc + (size_t)tile * B + bin, (tile == 0 ? st_inc : st_agg) | count);
+        const uint32_t count = tile_bytes(bin) >> 2;
+        st_relaxed_gpu(a.desc + (size_t)tile * B + bin, ((tile == 0 && !AGENT) ? st_inc : st_agg) | count);
         if (BULK) {
             // The destination of this tile's run of every bin must be known BEFORE the keys are ranked: the
             // run is laid out in shared memory at the 16-byte phase of its destination, so that its body is
@@ -314,10 +404,15 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         uint32_t c[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t row = 4u * lane + j;
-            const uint32_t w = (row < (uint32_t)ROWS) ? s_rowtot[row] : 0u;
-            c[2 * j] = w & 0xFFFFu;
-            c[2 * j + 1] = w >> 16;
+            if (WIDE) {
+                c[2 * j] = (8u * lane + 2 * j < (uint32_t)B) ? tile_bytes(8u * lane + 2 * j) : 0u;
+                c[2 * j + 1] = (8u * lane + 2 * j + 1 < (uint32_t)B) ? tile_bytes(8u * lane + 2 * j + 1) : 0u;
+            } else {
+                const uint32_t row = 4u * lane + j;
+                const uint32_t w = (row < (uint32_t)ROWS) ? s_rowtot[row] : 0u;
+                c[2 * j] = w & 0xFFFFu;
+                c[2 * j + 1] = w >> 16;
+            }
         }
         uint32_t phase[8];  // BULK: byte offset of the run's destination inside its 16-byte line
         uint32_t len[8];    // bytes the bin occupies in the reorder buffer (BULK: padded to whole 16-byte lines)
@@ -358,11 +453,21 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         const uint32_t it = tid + k * THREADS;
         if (it < (uint32_t)TR::SCAN_ITEMS) {
             const uint32_t row = it >> 2, g = it & 3u, par = row & 1u;
-            const uint2 bs = *reinterpret_cast<const uint2 *>(s_binstart + 2 * row);
-            const uint32_t base = (bs.x | (bs.y << 16)) + oct[k];  // byte positions < 2^16: no carry between the halves
+            uint32_t base;
+            if (WIDE) {
+                // absolute shared-memory address of the slot (pairs: half of it; the slot is 8 bytes)
+                // DUAL: {B's first position : A's first position} of the bin, B's keys after all of A's
+                if (DUAL) base = s_binstart[row] * 0x10001u + (s_rowtot[row] << 16) + oct[k];
+                else base = s_binstart[row] + oct[k] + (PAIRS ? sa_buf / 2u : sa_buf);
+            } else {
+                const uint2 bs = *reinterpret_cast<const uint2 *>(s_binstart + 2 * row);
+                base = (bs.x | (bs.y << 16)) + oct[k];  // byte positions < 2^16: no carry between the halves
+            }
             uint4 lo, hi;
+            {
             lo.x = base + ex[k][0]; lo.y = base + ex[k][1]; lo.z = base + ex[k][2]; lo.w = base + ex[k][3];
             hi.x = base + ex[k][4]; hi.y = base + ex[k][5]; hi.z = base + ex[k][6]; hi.w = base + ex[k][7];
+            }
             const uint32_t rb = sa_table + row * 128u + g * 32u;
             sm_st4(rb + par * 16u, par ? hi : lo);
             sm_st4(rb + (par ^ 1u) * 16u, par ? lo : hi);
@@ -373,7 +478,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     COL_STAMP(11);
 
     // ---- 4. rank + reorder: the warps take turns on the counter table -----------------------------
-    if (warp > 0) named_bar_sync(warp, 64);
+    if (warp != 0 && warp != WA) named_bar_sync(warp, 64);
     COL_STAMP(13);
 #pragma unroll
     for (int i0 = 0; i0 < ITEMS; i0 += GROUP) {
@@ -381,18 +486,40 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
 #pragma unroll
         for (int g = 0; g < GROUP; ++g)
             if (i0 + g < ITEMS) {
-                const uint32_t r = __funnelshift_r(key[i0 + g], key[i0 + g], rot_rank);
-                old[g] = sm_add_ret((r & m3) * 16u + sa_tlane, (r & 4u) * 0xFFFFu + 4u);
+                if (WIDE) {
+                    // During its turn the warp is the only one that touches the table, and a word belongs to one
+                    // lane: the fetch-and-add is a plain load followed by a reduction that does not wait for it
+                    // (a later load of the same word by the same thread observes the reduction: program order).
+                    const uint32_t slot = ((key[i0 + g] & mask4_rank) << 5) + sa_tlane;
+#ifdef B200_COL_LDRED
+                    old[g] = sm_ld(slot);
+                    sm_red(slot, gadd);
+#else
+                    old[g] = sm_add_ret(slot, gadd);
+#endif
+                } else {
+                    const uint32_t r = __funnelshift_r(key[i0 + g], key[i0 + g], rot_rank);
+                    old[g] = sm_add_ret((r & m3) * 16u + sa_tlane, (r & 4u) * 0xFFFFu + 4u);
+                }
             }
-        if (i0 + GROUP >= ITEMS && warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1u, 64);
+        if (i0 + GROUP >= ITEMS && warp + 1 < (uint32_t)WARPS && warp + 1 != WA) named_bar_arrive(warp + 1u, 64);
         if (i0 + GROUP >= ITEMS) COL_STAMP(14);
 #pragma unroll
         for (int g = 0; g < GROUP; ++g)
             if (i0 + g < ITEMS) {
-                const uint32_t r = __funnelshift_r(key[i0 + g], key[i0 + g], rot_rank);
-                const uint32_t pos = (r & 4u) ? (old[g] >> 16) : (old[g] & 0xFFFFu);
-                if (PAIRS) sm_st2(sa_buf + 2u * pos, key[i0 + g], val[i0 + g]);
-                else sm_st<0>(sa_buf + pos, key[i0 + g]);
+                if (DUAL) {
+                    const uint32_t pos = __byte_perm(old[g], 0u, gsel);
+                    if (PAIRS) sm_st2(sa_buf + 2u * pos, key[i0 + g], val[i0 + g]);
+                    else sm_st<0>(sa_buf + pos, key[i0 + g]);
+                } else if (WIDE) {
+                    if (PAIRS) sm_st2(2u * old[g], key[i0 + g], val[i0 + g]);
+                    else sm_st<0>(old[g], key[i0 + g]);
+                } else {
+                    const uint32_t r = __funnelshift_r(key[i0 + g], key[i0 + g], rot_rank);
+                    const uint32_t pos = (r & 4u) ? (old[g] >> 16) : (old[g] & 0xFFFFu);
+                    if (PAIRS) sm_st2(sa_buf + 2u * pos, key[i0 + g], val[i0 + g]);
+                    else sm_st<0>(sa_buf + pos, key[i0 + g]);
+                }
             }
     }
     COL_STAMP(15);
@@ -404,8 +531,71 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     constexpr int LB_WARPS = (WARPS - 1 < 4) ? WARPS - 1 : 4;
     constexpr int LBT = 32 * LB_WARPS;
     constexpr int NB = (B + LBT - 1) / LBT;
-    if (!BULK && tid < (uint32_t)LBT) {
-        const uint32_t u = tid;
+    // (DUAL: the first warps of both groups, in the order in which their turns end)
+    const uint32_t lb_slot = !DUAL ? warp : group_b ? 2u * (warp - WA) + 1u : (warp < (uint32_t)WARPS - WA ? 2u * warp : warp + ((uint32_t)WARPS - WA));
+    if constexpr (LBV4 && !BULK && !AGENT && (B % 4 == 0)) {
+        // Vector look-back: B / 4 threads, four neighbouring bins each, one 16-byte strong load per tile row (a warp
+        // issues one strong load per ~55 cycles, measured: the scalar walk spends most of its round on issuing them).
+        // The four bins of a thread consume the rows in order, each at its own position `pos`.
+        const uint32_t u = lb_slot * 32u + lane;
+        if (u < (uint32_t)B / 4u) {
+            uint32_t excl[4] = {0, 0, 0, 0};
+            int32_t pos[4];
+            bool done[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                pos[c] = (int32_t)tile - 1;
+                done[c] = (tile == 0);
+            }
+            bool all_done = (tile == 0);
+            while (!all_done) {
+                int32_t t0 = -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (!done[c]) t0 = max(t0, pos[c]);
+                uint4 v[LB];
+#pragma unroll
+                for (int k = 0; k < LB; ++k)
+                    v[k] = (t0 - k >= 0) ? ld_relaxed_gpu_v4(a.desc + (size_t)(t0 - k) * B + 4u * u) : make_uint4(st_not, st_not, st_not, st_not);
+                all_done = true;
+#pragma unroll
+                for (int k = 0; k < LB; ++k) {
+                    const uint32_t w4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t f = w4[c] & kDescFlagMask;
+                        if (!done[c] && pos[c] == t0 - k && f != st_not) {
+                            excl[c] += w4[c] & kDescValueMask;
+                            --pos[c];
+                            if (f == st_inc) done[c] = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) all_done = all_done && done[c];
+            }
+            uint32_t inc4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t bin = 4u * u + c;
+                const uint32_t count = tile_bytes(bin) >> 2;
+                const uint32_t bin_start = s_binstart[bin] >> 2;
+                inc4[c] = st_inc | (excl[c] + count);
+                const uint32_t first = a.bin_base[bin] + excl[c];
+                if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[bin] = first + count;
+                if (!DST) {
+                    s_gbase[bin] = first - bin_start;
+                } else {
+                    const uint64_t delta = 4ull * (uint64_t)first - 4ull * (uint64_t)bin_start;
+                    reinterpret_cast<uint64_t *>(s_gbase)[bin] = a.bin_dst[bin] + delta;
+                    if (PAIRS) reinterpret_cast<uint64_t *>(s_vbase)[bin] = a.bin_dst[B + bin] + delta;
+                }
+            }
+            if (tile != 0) st_relaxed_gpu_v4(a.desc + (size_t)tile * B + 4u * u, make_uint4(inc4[0], inc4[1], inc4[2], inc4[3]));
+        }
+    } else
+    if (!BULK && lb_slot < (uint32_t)LB_WARPS) {
+        const uint32_t u = lb_slot * 32u + lane;
         uint32_t excl[NB];
         int32_t t[NB];
         bool done[NB];
@@ -414,8 +604,23 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         for (int j = 0; j < NB; ++j) {
             excl[j] = 0;
             t[j] = (int32_t)tile - 1;
-            done[j] = (tile == 0) || (u + j * LBT >= (uint32_t)B);
+            done[j] = (tile == 0 && !AGENT) || (u + j * LBT >= (uint32_t)B);
             all_done = all_done && done[j];
+        }
+        if (AGENT) {
+            while (!all_done) {
+                all_done = true;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    if (done[j]) continue;
+                    const uint32_t w = ld_relaxed_gpu(a.desc + (size_t)tile * B + (u + j * LBT));
+                    if ((w & kDescFlagMask) == st_inc) {
+                        excl[j] = w & kDescValueMask;
+                        done[j] = true;
+                    }
+                    all_done = all_done && done[j];
+                }
+            }
         }
 #ifdef B200_COL_DEBUG
         long long dbg_rounds = 0;
@@ -457,9 +662,9 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         for (int j = 0; j < NB; ++j) {
             const uint32_t bin = u + j * LBT;
             if (bin < (uint32_t)B) {
-                const uint32_t count = ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu) >> 2;
+                const uint32_t count = tile_bytes(bin) >> 2;
                 const uint32_t bin_start = s_binstart[bin] >> 2;
-                if (tile != 0) st_relaxed_gpu(a.desc + (size_t)tile * B + bin, st_inc | (excl[j] + count));
+                if (tile != 0 && !AGENT) st_relaxed_gpu(a.desc + (size_t)tile * B + bin, st_inc | (excl[j] + count));
                 const uint32_t first = a.bin_base[bin] + excl[j];  // destination index of this tile's first key of the bin
                 if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[bin] = first + count;
                 if (!DST) {
@@ -482,12 +687,14 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     uint32_t *const kout = a.keys_out;
     uint32_t *const vout = a.vals_out;
     constexpr int kWG = 6;  // loads in flight per thread
+    auto digit4 = [&](uint32_t k) -> uint32_t { return WIDE ? (k & mask4) : (__funnelshift_r(k, k, rot_w) & mask4); };
+    auto original = [&](uint32_t k) -> uint32_t { return WIDE ? __funnelshift_l(k, k, rot_w) : k; };
     if (BULK) {
         // One thread per bin: the run [S, S + bytes) of the reorder buffer goes to its destination as
         // <= 3 head words, one bulk copy of whole 16-byte lines, <= 3 tail words.  The scatter stores were
         // made visible to the async proxy by the fence every thread executed before the barrier above.
         for (uint32_t bin = tid; bin < (uint32_t)B; bin += THREADS) {
-            uint32_t bytes = (s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu;
+            uint32_t bytes = tile_bytes(bin);
             if (!full && bin == a.mask) bytes -= 4u * ((uint32_t)TILE - n_valid);  // the padding keys sit at the end of the top bin
             if (bytes != 0u) {
                 const uint32_t src = sa_buf + s_binstart[bin];
@@ -521,12 +728,12 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             if (!DST) {
 #pragma unroll
                 for (int g = 0; g < kWG; ++g)
-                    if (k0 + g < ITEMS) gb[g] = sm_ld(sa_gbase + (__funnelshift_r(kk[g], kk[g], rot_w) & mask4));
+                    if (k0 + g < ITEMS) gb[g] = sm_ld(sa_gbase + digit4(kk[g]));
 #pragma unroll
                 for (int g = 0; g < kWG; ++g)
                     if (k0 + g < ITEMS) {
                         const uint32_t j = tid + (k0 + g) * THREADS;
-                        kout[gb[g] + j] = kk[g];
+                        kout[gb[g] + j] = original(kk[g]);
                         if (PAIRS) vout[gb[g] + j] = vv[g];
                     }
             } else {
@@ -534,9 +741,9 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
                 for (int g = 0; g < kWG; ++g)
                     if (k0 + g < ITEMS) {
                         const uint32_t j = tid + (k0 + g) * THREADS;
-                        const uint32_t d = (__funnelshift_r(kk[g], kk[g], rot_w) & mask4) >> 2;
+                        const uint32_t d = digit4(kk[g]) >> 2;
                         const uint64_t off = 4ull * j;
-                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = kk[g];
+                        *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_gbase)[d] + off) = original(kk[g]);
                         if (PAIRS)
                             *reinterpret_cast<uint32_t *>(reinterpret_cast<const uint64_t *>(s_vbase)[d] + off) = vv[g];
                     }
@@ -555,7 +762,8 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
                 } else {
                     kk = sm_ld(sa_buf + 4u * j);
                 }
-                const uint32_t d4 = __funnelshift_r(kk, kk, rot_w) & mask4;
+                const uint32_t d4 = digit4(kk);
+                kk = original(kk);
                 if (!DST) {
                     const uint32_t g = sm_ld(sa_gbase + d4) + j;
                     kout[g] = kk;

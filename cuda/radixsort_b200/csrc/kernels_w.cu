@@ -24,8 +24,13 @@ cudaError_t launch_col_variant(const PassArgs &a, cudaStream_t s) {
     constexpr int ITEMS = PAIRS ? g.items_pairs : g.items_keys;
     constexpr int WARPS = g.threads / 32;
     constexpr int GROUP = g.table_bits < ITEMS ? g.table_bits : ITEMS;
-    using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST>;
-    auto kernel = colsweep_pass_kernel<W, WARPS, ITEMS, g.min_ctas, g.lb_batch, GROUP, PAIRS, DST>;
+    constexpr bool WIDE = (g.mode == 4);
+    constexpr bool DUAL = WIDE && g.persist == 2;  // mode 4: persist = number of concurrent ranking chains (1 or 2)
+    using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST, WIDE, DUAL>;
+    constexpr bool AGENT = WIDE && g.lb_batch == 0;  // mode 4, lb_batch 0: a scan agent CTA instead of per-tile look-back
+    constexpr bool LBV4 = WIDE && g.lb_batch >= 32;  // mode 4, lb_batch 32 + d: 16-byte look-back loads, d rows in flight
+    constexpr int LBD = AGENT ? 1 : LBV4 ? g.lb_batch - 32 : g.lb_batch;
+    auto kernel = colsweep_pass_kernel<W, WARPS, ITEMS, g.min_ctas, LBD, GROUP, PAIRS, DST, WIDE, DUAL, AGENT, LBV4>;
     static std::atomic<uint64_t> configured{0};  // one bit per device: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -35,7 +40,7 @@ cudaError_t launch_col_variant(const PassArgs &a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    kernel<<<a.num_tiles, g.threads, TR::SMEM_BYTES, s>>>(a);
+    kernel<<<a.num_tiles + (AGENT ? 1u : 0u), g.threads, TR::SMEM_BYTES, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -75,7 +80,7 @@ cudaError_t launch_one_variant(const PassArgs &a, cudaStream_t s) {
 
 template <int V, bool PAIRS, bool DST>
 cudaError_t launch_variant(const PassArgs &a, cudaStream_t s) {
-    if constexpr (kVariants[V].mode == 3) return launch_col_variant<V, PAIRS, DST>(a, s);
+    if constexpr (kVariants[V].mode >= 3) return launch_col_variant<V, PAIRS, DST>(a, s);
     else return launch_one_variant<V, PAIRS, DST>(a, s);
 }
 
@@ -176,6 +181,48 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 47: return launch_modes<47>(pairs, dst, a, s);
     case 48: return launch_modes<48>(pairs, dst, a, s);
     case 49: return launch_modes<49>(pairs, dst, a, s);
+    case 50: return launch_modes<50>(pairs, dst, a, s);
+    case 51: return launch_modes<51>(pairs, dst, a, s);
+    case 52: return launch_modes<52>(pairs, dst, a, s);
+    case 53: return launch_modes<53>(pairs, dst, a, s);
+    case 54: return launch_modes<54>(pairs, dst, a, s);
+    case 55: return launch_modes<55>(pairs, dst, a, s);
+    case 56: return launch_modes<56>(pairs, dst, a, s);
+    case 57: return launch_modes<57>(pairs, dst, a, s);
+    case 58: return launch_modes<58>(pairs, dst, a, s);
+    case 59: return launch_modes<59>(pairs, dst, a, s);
+    case 60: return launch_modes<60>(pairs, dst, a, s);
+    case 61: return launch_modes<61>(pairs, dst, a, s);
+    case 62: return launch_modes<62>(pairs, dst, a, s);
+    case 63: return launch_modes<63>(pairs, dst, a, s);
+    case 64: return launch_modes<64>(pairs, dst, a, s);
+    case 65: return launch_modes<65>(pairs, dst, a, s);
+    case 66: return launch_modes<66>(pairs, dst, a, s);
+    case 67: return launch_modes<67>(pairs, dst, a, s);
+    case 68: return launch_modes<68>(pairs, dst, a, s);
+    case 69: return launch_modes<69>(pairs, dst, a, s);
+    case 70: return launch_modes<70>(pairs, dst, a, s);
+    case 71: return launch_modes<71>(pairs, dst, a, s);
+    case 72: return launch_modes<72>(pairs, dst, a, s);
+    case 73: return launch_modes<73>(pairs, dst, a, s);
+    case 74: return launch_modes<74>(pairs, dst, a, s);
+    case 75: return launch_modes<75>(pairs, dst, a, s);
+    case 76: return launch_modes<76>(pairs, dst, a, s);
+    case 77: return launch_modes<77>(pairs, dst, a, s);
+    case 78: return launch_modes<78>(pairs, dst, a, s);
+    case 79: return launch_modes<79>(pairs, dst, a, s);
+    case 80: return launch_modes<80>(pairs, dst, a, s);
+    case 81: return launch_modes<81>(pairs, dst, a, s);
+    case 82: return launch_modes<82>(pairs, dst, a, s);
+    case 83: return launch_modes<83>(pairs, dst, a, s);
+    case 84: return launch_modes<84>(pairs, dst, a, s);
+    case 85: return launch_modes<85>(pairs, dst, a, s);
+    case 86: return launch_modes<86>(pairs, dst, a, s);
+    case 87: return launch_modes<87>(pairs, dst, a, s);
+    case 88: return launch_modes<88>(pairs, dst, a, s);
+    case 89: return launch_modes<89>(pairs, dst, a, s);
+    case 90: return launch_modes<90>(pairs, dst, a, s);
+    case 91: return launch_modes<91>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -13,12 +13,12 @@ struct PassVariant {
     int items_keys;
     int items_pairs;
     int min_ctas;
-    int mode;        // 0 table rank, 1 atomic rank, 2 match.any (onesweep.cuh); 3 = column sweep (colsweep.cuh)
+    int mode;        // 0 table rank, 1 atomic rank, 2 match.any (onesweep.cuh); 3 = column sweep (colsweep.cuh), 4 = with 32-bit counters
     int table_bits;  // mode 0: bits of the peer table; mode 3: ranking atomics in flight per thread
     int lb_batch;  // look-back descriptors in flight per bin thread
-    int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA
+    int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA; mode 4: concurrent ranking chains (2 = two warp groups)
 };
-constexpr int kNumVariants = 50;
+constexpr int kNumVariants = 92;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -71,6 +71,52 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {224, 36, 20, 4, 3, 12, 4, 0},  // 47 seven warps, four CTAs per SM
     {160, 68, 36, 3, 3, 17, 4, 0},  // 48 five warps x 68 keys, three CTAs per SM
     {96, 84, 44, 5, 3, 14, 4, 0},   // 49 three warps x 84 keys, five CTAs per SM
+    // column sweep with 32-bit counters (mode 4): 32 KB table, larger tiles, two CTAs per SM
+    {288, 52, 28, 2, 4, 26, 4, 0},  // 50
+    {288, 52, 28, 2, 4, 52, 4, 0},  // 51 = 50, a whole turn in flight
+    {416, 36, 20, 2, 4, 36, 4, 0},  // 52 thirteen warps x 36 keys
+    {288, 60, 28, 2, 4, 20, 4, 0},  // 53
+    {352, 44, 20, 2, 4, 22, 4, 0},  // 54 eleven warps x 44 keys
+    {288, 36, 20, 2, 4, 36, 4, 0},  // 55
+    // mode 4 with persist = 2: two 16-bit counters per word, the two halves of the warps rank concurrently
+    {320, 44, 20, 2, 4, 22, 4, 2},  // 56 ten warps (5 + 5) x 44 keys
+    {320, 44, 20, 2, 4, 11, 4, 2},  // 57
+    {320, 44, 20, 2, 4, 44, 4, 2},  // 58 a whole turn in flight
+    {256, 60, 28, 2, 4, 20, 4, 2},  // 59 eight warps (5 + 3) x 60 keys, 128 registers
+    {192, 76, 36, 2, 4, 19, 4, 2},  // 60 six warps (3 + 3) x 76 keys
+    {448, 28, 12, 2, 4, 14, 4, 2},  // 61 fourteen warps (7 + 7) x 28 keys
+    {320, 36, 20, 2, 4, 18, 4, 2},  // 62 ten warps x 36 keys
+    {384, 36, 20, 2, 4, 18, 4, 2},  // 63 twelve warps (7 + 5) x 36 keys
+    {256, 60, 28, 2, 4, 20, 8, 2},  // 64 = 59, 8-deep look-back
+    {256, 60, 28, 2, 4, 20, 16, 2}, // 65 = 59, 16-deep look-back
+    {256, 60, 28, 2, 4, 30, 8, 2},  // 66
+    {320, 44, 20, 2, 4, 22, 8, 2},  // 67 = 56, 8-deep look-back
+    {320, 44, 20, 2, 4, 22, 16, 2}, // 68
+    {256, 52, 28, 2, 4, 26, 8, 2},  // 69
+    {192, 76, 36, 2, 4, 19, 8, 2},  // 70
+    {256, 60, 28, 2, 4, 20, 12, 2}, // 71
+    {256, 36, 20, 3, 4, 18, 4, 2},  // 72 three CTAs per SM
+    {256, 36, 20, 3, 4, 18, 8, 2},  // 73
+    {192, 44, 20, 3, 4, 22, 4, 2},  // 74 six warps (3 + 3) x 44 keys, three CTAs per SM
+    {320, 28, 12, 3, 4, 14, 4, 2},  // 75 ten warps x 28 keys, three CTAs per SM
+    // mode 4 with lb_batch = 0: CTA 0 is a scan agent that turns the tiles' aggregates into exclusive prefixes
+    {256, 60, 28, 2, 4, 20, 0, 2},  // 76 = 59 with the agent
+    {320, 44, 20, 2, 4, 22, 0, 2},  // 77 = 56 with the agent
+    {256, 60, 28, 2, 4, 30, 0, 2},  // 78
+    {192, 76, 36, 2, 4, 19, 0, 2},  // 79
+    {288, 52, 28, 2, 4, 26, 0, 0},  // 80 = 50 (one chain) with the agent
+    {352, 44, 20, 2, 4, 22, 0, 0},  // 81 = 54 (one chain) with the agent
+    {256, 36, 20, 3, 4, 18, 0, 2},  // 82 = 72 with the agent
+    {256, 52, 28, 2, 4, 26, 0, 2},  // 83
+    // mode 4 with lb_batch = 32 + d: look-back with 16-byte strong loads (four bins per thread), d rows in flight
+    {256, 60, 28, 2, 4, 20, 36, 2}, // 84 = 59, d = 4
+    {256, 60, 28, 2, 4, 20, 40, 2}, // 85 d = 8
+    {256, 60, 28, 2, 4, 20, 44, 2}, // 86 d = 12
+    {256, 60, 28, 2, 4, 20, 48, 2}, // 87 d = 16
+    {320, 44, 20, 2, 4, 22, 40, 2}, // 88 = 56, d = 8
+    {320, 44, 20, 2, 4, 22, 48, 2}, // 89 d = 16
+    {352, 44, 20, 2, 4, 22, 40, 0}, // 90 = 54 (one chain), d = 8
+    {192, 76, 36, 2, 4, 19, 40, 2}, // 91 = 60, d = 8
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

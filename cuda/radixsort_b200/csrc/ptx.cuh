@@ -27,6 +27,16 @@ __device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Four consecutive descriptors (16-byte aligned) in one request; every element is its own relaxed access.
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t *p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Streaming (read-once) key loads: evict-first so descriptors and partially written output
 // sectors keep their place in L2.
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
@@ -59,6 +69,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {  // release.cta
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(
