@@ -39,6 +39,7 @@ struct Params {
     std::atomic<int> dst_bulk{1};        // digit pass with per-bin destinations, keys only: bulk-copy write-out
     std::atomic<int> host_overlap{1};    // host-pointer path: chunked upload + MSD split + per-bucket download
     std::atomic<int> scan_variant{8};    // tile geometry of b200sort_exclusive_scan (scan.cuh: kScanGeom)
+    std::atomic<int> prefetch_tiles{-1}; // column sweep: L2 prefetch distance in tiles; -1 = one tile per SM ahead, 0 = off
 } g_params;
 
 // Per CUDA ordinal: the sm_100 check, the SM count and the verdict of the RANK_ATOMIC self test
@@ -57,6 +58,10 @@ DeviceState &dev_state() {
     return g_dev[dev & (kMaxDevices - 1)];
 }
 int num_sms() { return dev_state().sms.load(); }
+uint32_t prefetch_distance() {
+    const int p = g_params.prefetch_tiles;
+    return (uint32_t)(p >= 0 ? p : num_sms());
+}
 
 int fail(int code, const char *what) {
     g_last_error = std::string(what) + ": " + b200sort_error_string(code);
@@ -193,17 +198,14 @@ int run_selftest() {
     return st.atomic_rank_ok;
 }
 
-// Automatic choice: the fastest measured geometry (profiles/r01_sweep_*.jsonl) in atomic-rank mode
-// when the device passed the self test, else the table-rank default.
-constexpr int kAutoVariantW8 = 10;       // keys: 256 threads x 44 keys, three CTAs per SM
-constexpr int kAutoVariantW8Pairs = 35;  // pairs: 256 threads x 36 pairs, two CTAs per SM
-
+// Automatic choice: the fastest measured kernel (profiles/r02_sweep_*.jsonl).  Digits of >= 4 bits: the column
+// sweep with two ranking chains (kDualVariant; keys and pairs; spec-safe, no self test involved); narrower
+// digits: ballot rank.  The atomic-rank kernels of round 1 (variants 1, 10, 35) stay selectable by number.
 int effective_variant(int width, bool pairs = false) {
     int v = g_params.variant;
     const int narrow = g_params.narrow_variant;
-    if (v < 0)
-        v = (width == 8) ? (pairs ? kAutoVariantW8Pairs : kAutoVariantW8)
-                         : (width <= 3 ? (narrow >= 0 ? narrow : kBallotVariant) : 1);
+    (void)pairs;
+    if (v < 0) v = (width >= 4) ? kDualVariant : (narrow >= 0 ? narrow : kBallotVariant);
     if (!variant_available(width, v)) v = fallback_variant(width);
     // Atomic-rank kernels need same-address shared atomics of one warp instruction to be applied in lane
     // order (not promised by PTX): they run only on a device that passed the self test, and never when
@@ -359,6 +361,7 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
             a.shift = pl.shift[p];
             a.mask = (1u << pl.bits[p]) - 1u;
             a.parity = (uint32_t)(p & 1);
+            a.prefetch = prefetch_distance();
             CU(launch_pass(pl.width, variant, pairs, false, a, stream));
         }
         CU(profile_mark(stream, p + 1));
@@ -592,6 +595,7 @@ int sort_host_overlapped(const uint32_t *hk_in, const uint32_t *hv_in, uint64_t 
         a.shift = 32 - kMsdBits;
         a.mask = B - 1;
         a.parity = 0;
+        a.prefetch = prefetch_distance();
         CU(launch_pass(kMsdBits, variant, pairs, false, a, s));
     }
     CU(cudaStreamSynchronize(s));  // bucket sizes are on the host now (the upload is complete as well)
@@ -784,6 +788,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.scan_variant = value;
         return 0;
     }
+    if (!strcmp(name, "prefetch_tiles")) {
+        if (value < -1 || value > (1 << 20)) return B200SORT_EINVAL;
+        g_params.prefetch_tiles = value;
+        return 0;
+    }
     return B200SORT_EINVAL;
 }
 
@@ -797,6 +806,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "tuning_build")) return kTuningBuild ? 1 : 0;
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
     if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
+    if (!strcmp(name, "prefetch_tiles")) return g_params.prefetch_tiles;
     if (!strcmp(name, "host_overlap")) return g_params.host_overlap;
     if (!strcmp(name, "dst_bulk")) return g_params.dst_bulk;
     if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
@@ -983,6 +993,7 @@ int b200sort_digit_pass(const uint32_t *d_keys_in, const uint32_t *d_vals_in, ui
         a.shift = (uint32_t)shift;
         a.mask = (1u << std::min(bits, 32 - shift)) - 1u;
         a.parity = 0;
+        a.prefetch = prefetch_distance();
         CU(launch_pass(bits, variant, pairs, dst, a, s));
     }
     return 0;

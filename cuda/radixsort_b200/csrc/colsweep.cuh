@@ -271,6 +271,14 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
 #endif
                          ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0) &&
                          (!PAIRS || (reinterpret_cast<uintptr_t>(a.vals_in) & 15u) == 0);
+    // The SM slot that runs this tile runs tile + (resident CTAs) next: its keys are requested into L2 now, so
+    // that the bulk load of that tile is an L2 hit (measured: 0.570 -> 0.548 ms per pass).
+    if (WIDE && tid == 32 && a.prefetch != 0u && tile + a.prefetch < a.num_tiles - 1u &&
+        ((reinterpret_cast<uintptr_t>(a.keys_in) & 15u) == 0) && (!PAIRS || (reinterpret_cast<uintptr_t>(a.vals_in) & 15u) == 0)) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.keys_in + (size_t)(tile + a.prefetch) * TILE), "r"((uint32_t)TILE * 4u) : "memory");
+        if (PAIRS)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.vals_in + (size_t)(tile + a.prefetch) * TILE), "r"((uint32_t)TILE * 4u) : "memory");
+    }
     if (use_tma && tid == 0) {
         mbar_init(s_bar, 1);
         fence_mbar_init();
@@ -548,7 +556,13 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
                 done[c] = (tile == 0);
             }
             bool all_done = (tile == 0);
+#ifdef B200_COL_DEBUG
+            long long dbg_rounds = 0;
+#endif
             while (!all_done) {
+#ifdef B200_COL_DEBUG
+                ++dbg_rounds;
+#endif
                 int32_t t0 = -1;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
@@ -574,6 +588,12 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
 #pragma unroll
                 for (int c = 0; c < 4; ++c) all_done = all_done && done[c];
             }
+#ifdef B200_COL_DEBUG
+            if (blockIdx.x == a.num_tiles / 2 && (threadIdx.x & 31u) == 0) {
+                g_col_dbg[(threadIdx.x >> 5) * 20 + 18] = dbg_rounds;
+                g_col_dbg[(threadIdx.x >> 5) * 20 + 19] = (long long)tile - 1 - pos[0];
+            }
+#endif
             uint32_t inc4[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {

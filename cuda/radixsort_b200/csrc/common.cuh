@@ -51,6 +51,7 @@ struct PassArgs {
     uint32_t shift;
     uint32_t mask;
     uint32_t parity;           // launch parity: rotates the descriptor status codes
+    uint32_t prefetch;         // column sweep: the tile this many tiles ahead is prefetched into L2 (0 = off)
 };
 
 // Block-wide exclusive scan of one value per thread for the first `active_warps` warps

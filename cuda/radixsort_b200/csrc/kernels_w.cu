@@ -135,6 +135,7 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case kBallotVariant: return launch_modes<kBallotVariant>(pairs, dst, a, s);
     case kBallotSmallVariant: return launch_modes<kBallotSmallVariant>(pairs, dst, a, s);
     case kColVariant: return launch_modes<kColVariant>(pairs, dst, a, s);
+    case kDualVariant: return launch_modes<kDualVariant>(pairs, dst, a, s);
 #if B200_W == 8
     case 2: return launch_modes<2>(pairs, dst, a, s);
     case 3: return launch_modes<3>(pairs, dst, a, s);
@@ -223,6 +224,23 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 89: return launch_modes<89>(pairs, dst, a, s);
     case 90: return launch_modes<90>(pairs, dst, a, s);
     case 91: return launch_modes<91>(pairs, dst, a, s);
+    case 92: return launch_modes<92>(pairs, dst, a, s);
+    case 93: return launch_modes<93>(pairs, dst, a, s);
+    case 94: return launch_modes<94>(pairs, dst, a, s);
+    case 96: return launch_modes<96>(pairs, dst, a, s);
+    case 97: return launch_modes<97>(pairs, dst, a, s);
+    case 98: return launch_modes<98>(pairs, dst, a, s);
+    case 99: return launch_modes<99>(pairs, dst, a, s);
+    case 100: return launch_modes<100>(pairs, dst, a, s);
+    case 101: return launch_modes<101>(pairs, dst, a, s);
+    case 102: return launch_modes<102>(pairs, dst, a, s);
+    case 103: return launch_modes<103>(pairs, dst, a, s);
+    case 104: return launch_modes<104>(pairs, dst, a, s);
+    case 105: return launch_modes<105>(pairs, dst, a, s);
+    case 106: return launch_modes<106>(pairs, dst, a, s);
+    case 107: return launch_modes<107>(pairs, dst, a, s);
+    case 108: return launch_modes<108>(pairs, dst, a, s);
+    case 109: return launch_modes<109>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

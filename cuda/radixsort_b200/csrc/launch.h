@@ -18,7 +18,7 @@ struct PassVariant {
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA; mode 4: concurrent ranking chains (2 = two warp groups)
 };
-constexpr int kNumVariants = 92;
+constexpr int kNumVariants = 110;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -117,6 +117,24 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {320, 44, 20, 2, 4, 22, 48, 2}, // 89 d = 16
     {352, 44, 20, 2, 4, 22, 40, 0}, // 90 = 54 (one chain), d = 8
     {192, 76, 36, 2, 4, 19, 40, 2}, // 91 = 60, d = 8
+    {256, 60, 28, 2, 4, 20, 34, 2}, // 92 = 84, d = 2
+    {256, 60, 28, 2, 4, 20, 35, 2}, // 93 d = 3
+    {256, 60, 28, 2, 4, 20, 38, 2}, // 94 d = 6
+    {256, 60, 36, 2, 4, 10, 36, 2}, // 95 10 atomics in flight; 36 pairs per thread -- the default (kDualVariant)
+    {256, 60, 28, 2, 4, 15, 36, 2}, // 96
+    {256, 60, 28, 2, 4, 30, 36, 2}, // 97
+    {256, 60, 28, 2, 4, 60, 36, 2}, // 98 a whole turn in flight
+    {256, 52, 28, 2, 4, 26, 36, 2}, // 99
+    {256, 44, 20, 2, 4, 22, 36, 2}, // 100
+    {256, 44, 20, 3, 4, 22, 36, 2}, // 101 44 keys, three CTAs per SM
+    {256, 36, 20, 3, 4, 18, 36, 2}, // 102
+    {192, 76, 36, 2, 4, 19, 36, 2}, // 103 six warps (3 + 3)
+    {320, 44, 20, 2, 4, 22, 36, 2}, // 104 ten warps (5 + 5)
+    {384, 36, 20, 2, 4, 18, 36, 2}, // 105 twelve warps (7 + 5)
+    {352, 44, 20, 2, 4, 22, 36, 0}, // 106 one chain, eleven warps
+    {256, 60, 28, 2, 4, 12, 36, 2}, // 107
+    {256, 60, 36, 2, 4, 10, 36, 2}, // 108 = 95 with 36 pairs per thread
+    {256, 60, 36, 2, 4, 10, 34, 2}, // 109
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
@@ -139,8 +157,10 @@ constexpr bool kTuningBuild = true;
 #else
 constexpr bool kTuningBuild = false;
 #endif
+constexpr int kDualVariant = 95;  // column sweep, 32-bit counter words, two ranking chains: keys, digits of >= 4 bits
 constexpr bool variant_compiled(int width, int variant) {
     if (variant == kColVariant) return true;
+    if (variant == kDualVariant && width >= 4) return true;
     if (kTuningBuild)
         return variant == 0 || variant == 1 || variant == kBallotVariant || variant == kBallotSmallVariant ||
                (width == 8 && variant > 0 && variant < kNumVariants);
@@ -154,7 +174,8 @@ inline int fallback_variant(int width) { return width <= 3 ? kBallotVariant : 1;
 // variants that are instantiated with per-bin destinations (b200sort_digit_pass with d_bin_dst)
 constexpr bool variant_has_dst(int width, int variant) {
     return variant_compiled(width, variant) &&
-           (variant <= 1 || variant == kBallotVariant || variant == kBallotSmallVariant || variant == kColVariant);
+           (variant <= 1 || variant == kBallotVariant || variant == kBallotSmallVariant || variant == kColVariant ||
+            variant == kDualVariant);
 }
 
 #define B200_DECLARE_W(w)                                                                        \

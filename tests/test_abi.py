@@ -88,7 +88,7 @@ def test_argument_errors_without_touching_the_gpu(rs):
     assert lib.b200sort_mgpu_keys_host(a.ctypes.data, 16, o.ctypes.data, 8, 0, None, 2) == -1
     assert lib.b200sort_mgpu_last_stats(None, 0) == 0
     assert lib.b200sort_mgpu_shutdown() == 0
-    assert lib.b200sort_set_param(b"variant", 99) == -1
+    assert lib.b200sort_set_param(b"variant", 9999) == -1
     assert lib.b200sort_set_param(b"variant", -1) == 0     # automatic choice
     assert lib.b200sort_set_param(b"no_such_param", 1) == -1
     assert b"invalid" in lib.b200sort_error_string(-1)

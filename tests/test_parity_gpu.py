@@ -245,7 +245,8 @@ def test_multi_launch_portions(rs, oracle):
 
 def _variants_in_this_build():
     """Every geometry of csrc/launch.h with the tuning build (B200_TUNING=1), else the kernels the product
-    library carries for the 8-bit digit: atomic rank (1, 10; 35 for pairs) and the column sweep (36)."""
+    library carries for the 8-bit digit: atomic rank (1, 10; 35 for pairs), the column sweep (36) and the default,
+    the column sweep with two ranking chains (95)."""
     if os.environ.get("B200_TUNING"):
         try:
             import ctypes
@@ -255,7 +256,7 @@ def _variants_in_this_build():
                 return list(range(lib.b200sort_get_param(b"num_variants")))
         except (OSError, RuntimeError):
             pass
-    return [1, 10, 35, 36]
+    return [1, 10, 35, 36, 95]
 
 
 @pytest.mark.parametrize("variant", _variants_in_this_build())
@@ -303,14 +304,21 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
         rs.set_param("variant", -1)
 
 
-def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle):
+@pytest.mark.parametrize("kernel", ["colsweep", "default"])
+def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle, kernel):
     """safe_rank=1 confines the library to kernels whose ranking follows from the PTX memory model: the
     column-sweep kernel (lane-private counters, warp turns ordered by named barriers) replaces every
-    atomic-rank variant, for every digit width, for pairs and for per-bin destinations."""
+    atomic-rank variant, for every digit width, for pairs and for per-bin destinations.  The default kernel
+    (the column sweep with two chains, variant 95, digits of >= 4 bits) is such a kernel itself and stays."""
     rs.set_param("safe_rank", 1)
+    if kernel == "colsweep":
+        rs.set_param("variant", 1)      # an atomic-rank request: replaced by the column sweep, variant 36
     try:
         assert rs.get_param("safe_rank") == 1
-        assert rs.get_param("effective_variant") == 36 and rs.get_param("rank_mode") == 3
+        if kernel == "colsweep":
+            assert rs.get_param("effective_variant") == 36 and rs.get_param("rank_mode") == 3
+        else:
+            assert rs.get_param("effective_variant") == 95 and rs.get_param("rank_mode") == 4
         n = (1 << 19) + 4321
         k = oracle.generate("uniform", n)
         z = oracle.generate("zipf", n)
@@ -324,15 +332,44 @@ def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle):
         for kind in ("all_equal", "unique16", "sorted", "iota"):
             kk = oracle.generate(kind, n)
             assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), kind
-        for m in (1, 2, 31, 33, 10367, 10368, 10369, 2 * 10368 + 1):     # around the 10368-key tile
+        for m in (1, 2, 31, 33, 10367, 10368, 10369, 2 * 10368 + 1,     # around the 10368- and 15360-key tiles
+                  15359, 15360, 15361, 2 * 15360 + 1, 9216, 9217):      # (and the 9216-pair tile)
             kk = oracle.generate("uniform", m)
             assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), m
         # unaligned input (no bulk copy): same answer
         import torch
         d = to_dev(np.concatenate([np.zeros(1, np.uint32), k]))[1:]
         assert np.array_equal(to_host(rs.sort_keys(d, 8)), oracle.sort_keys(k, 8))
+        dv = to_dev(np.concatenate([np.zeros(1, np.uint32), v]))[1:]
+        ko, vo = rs.sort_pairs(d, dv, 8)
+        rk, rv = oracle.sort_pairs(k, v, 8)
+        assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv)
     finally:
         rs.set_param("safe_rank", 0)
+        rs.set_param("variant", -1)
+
+
+@pytest.mark.parametrize("offset_words", [0, 1, 2, 3])
+def test_unaligned_arrays_with_a_short_prefetch_distance(rs, oracle, offset_words):
+    """The default kernel asks the copy engine to bring a later tile into L2 (16-byte aligned requests only):
+    with a distance of one tile every launch of a small sort exercises it; arrays that start 4, 8 or 12 bytes
+    off a 16-byte boundary must take the plain path (regression: the host path sorts buckets in place at
+    arbitrary offsets)."""
+    rs.set_param("prefetch_tiles", 1)
+    try:
+        n = 5 * 15360 + 777
+        k = oracle.generate("uniform", n)
+        v = np.arange(n, dtype=np.uint32)
+        pad = np.zeros(offset_words, np.uint32)
+        d = to_dev(np.concatenate([pad, k]))[offset_words:]
+        dv = to_dev(np.concatenate([pad, v]))[offset_words:]
+        for nbits in (8, 4):
+            assert np.array_equal(to_host(rs.sort_keys(d, nbits)), oracle.sort_keys(k, nbits))
+            ko, vo = rs.sort_pairs(d, dv, nbits)
+            rk, rv = oracle.sort_pairs(k, v, nbits)
+            assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv)
+    finally:
+        rs.set_param("prefetch_tiles", -1)
 
 
 def test_histogram_matches_tile_table_column_sums(rs, oracle):

@@ -19,7 +19,8 @@ from conftest import to_dev, to_host
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [28, 10, 36])   # tiny tiles (ballot rank), default (atomic rank), column sweep
+# tiny tiles (ballot rank), atomic rank, column sweep, column sweep with two chains and vector look-back (default)
+@pytest.mark.parametrize("variant", [28, 10, 36, 95])
 def test_look_back_litmus_many_small_launches_on_concurrent_streams(rs, oracle, variant):
     import torch
     rs.set_param("variant", variant)
@@ -79,5 +80,11 @@ def test_atomic_order_selftest_runs_on_every_visible_device(rs):
             verdicts.append(rs.get_param("atomic_rank_ok"))
     assert all(v in (0, 1) for v in verdicts)
     with torch.cuda.device(0):
-        # the verdict decides the kernel: atomic rank (mode 1) only on a device that passed
-        assert rs.get_param("rank_mode") == (1 if verdicts[0] == 1 else 3)
+        # the default kernel does not depend on the verdict (column sweep with two chains, mode 4) ...
+        assert rs.get_param("rank_mode") == 4
+        # ... and an atomic-rank request (mode 1) is honoured only on a device that passed
+        rs.set_param("variant", 10)
+        try:
+            assert rs.get_param("rank_mode") == (1 if verdicts[0] == 1 else 3)
+        finally:
+            rs.set_param("variant", -1)

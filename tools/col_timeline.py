@@ -16,6 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", type=int, default=36)
     ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--reps", type=int, default=1)
     args = ap.parse_args()
     rs.load()
     lib = ctypes.CDLL(_lib.LIB_PATH)
@@ -24,12 +25,19 @@ def main():
     out = torch.empty_like(keys)
     ws = rs.Workspace("cuda")
     rs.set_param("variant", args.variant)
-    for _ in range(3):
+    for rep in range(args.reps):
+      for _ in range(3):
         rs.sort_keys(keys, 8, out=out, workspace=ws)
-    torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * 320)()
-    rc = lib.b200sort_debug_read(buf)
-    assert rc == 0, rc
+      torch.cuda.synchronize()
+      buf = (ctypes.c_longlong * 320)()
+      rc = lib.b200sort_debug_read(buf)
+      assert rc == 0, rc
+      if rep + 1 < args.reps:
+        t0 = min(buf[w * 20] for w in range(16) if buf[w * 20])
+        print(json.dumps({"rep": rep, "chain_end": max(buf[w * 20 + 14] for w in range(16)) - t0,
+                          "lookback_end": max(buf[w * 20 + 12] for w in range(16) if buf[w * 20]) - t0,
+                          "end": max(buf[w * 20 + 17] for w in range(16)) - t0,
+                          "lb_rounds": max(buf[w * 20 + 18] for w in range(16)), "lb_walk": max(buf[w * 20 + 19] for w in range(16))}))
     t0 = min(buf[w * 20] for w in range(16) if buf[w * 20])
     for w in range(16):
         if not buf[w * 20]:
