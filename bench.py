@@ -301,7 +301,8 @@ def run_single(args):
     pass_avg = sum(pass_ms) / max(1, len(pass_ms))
     achieved = bytes_per_key * n / (pass_avg * 1e-3) / 1e9 if pass_ms else None
     eff_variant = rs.get_param("effective_variant") if not pairs else None
-    kernel_name = "onesweep_pass_kernel"
+    # the digit-pass kernel in effect: the column sweep (csrc/colsweep.cuh, rank modes 3 and 4) or onesweep.cuh
+    kernel_name = "colsweep_pass_kernel" if rs.get_param("rank_mode") >= 3 else "onesweep_pass_kernel"
     roofline = {
         "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": (achieved / peak) if achieved else None,

@@ -495,16 +495,8 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         for (int g = 0; g < GROUP; ++g)
             if (i0 + g < ITEMS) {
                 if (WIDE) {
-                    // During its turn the warp is the only one that touches the table, and a word belongs to one
-                    // lane: the fetch-and-add is a plain load followed by a reduction that does not wait for it
-                    // (a later load of the same word by the same thread observes the reduction: program order).
                     const uint32_t slot = ((key[i0 + g] & mask4_rank) << 5) + sa_tlane;
-#ifdef B200_COL_LDRED
-                    old[g] = sm_ld(slot);
-                    sm_red(slot, gadd);
-#else
                     old[g] = sm_add_ret(slot, gadd);
-#endif
                 } else {
                     const uint32_t r = __funnelshift_r(key[i0 + g], key[i0 + g], rot_rank);
                     old[g] = sm_add_ret((r & m3) * 16u + sa_tlane, (r & 4u) * 0xFFFFu + 4u);
