@@ -45,6 +45,19 @@
 // and keeps the worst regular input -- all keys equal: lane l stores to position l*COL + r -- at a
 // 4-way bank conflict, the same as random positions.
 //
+// The default form since round 2 (template flags WIDE + DUAL + LBV4, launch.h: kDualVariant) changes three things,
+// each after a measurement (tools/gpu_probe3.cu, tools/col_timeline.py, profiles/r02_probe3_b200.json):
+//   * A warp's shared-memory atomics WITH a return value complete one after the other -- 16.5 cycles each, whatever
+//     else the SM does -- while those of different warps overlap perfectly.  One chain of turns therefore ranks one
+//     key per lane per 16.5 cycles, as fast as the whole SM may take per 32 keys at 70 % of HBM bandwidth.  DUAL
+//     splits the tile into two halves with their own column sets, chains and 16-bit counter halves of one 32-bit
+//     word per (bin, lane) (row = digit: no per-key half select, constant addend); keys stay rotated from load to
+//     write-out.  8 warps as 5 + 3, 60 keys per thread, 128 registers, two CTAs per SM.
+//   * A warp issues one strong (.relaxed.gpu) load per ~55 cycles, so a look-back round of 2 bins x 4 rows per
+//     thread was mostly issue time.  LBV4: 64 threads, four neighbouring bins each, 16-byte strong loads.
+//   * The tile this SM slot runs next (PassArgs::prefetch tiles ahead) is requested into L2 when a tile starts.
+// 0.636 -> 0.545 ms per pass for 2^28 keys (0.60 of measured HBM peak), 0.475 ms with 4-bit digits (0.69).
+//
 // Descriptor protocol, ragged last tile, per-bin destinations (DST) and the carry between launches
 // of one pass are those of onesweep.cuh.
 #pragma once
@@ -153,7 +166,7 @@ __device__ __forceinline__ uint32_t look_back_one_bin(const uint32_t *desc, uint
     return excl;
 }
 
-template <int W, int WARPS, int ITEMS, int MIN_CTAS, int LB, int GROUP, bool PAIRS, bool DST, bool WIDE = false, bool DUAL = false, bool AGENT = false, bool LBV4 = false>
+template <int W, int WARPS, int ITEMS, int MIN_CTAS, int LB, int GROUP, bool PAIRS, bool DST, bool WIDE = false, bool DUAL = false, bool LBV4 = false>
 __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(const PassArgs a) {
     using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST, WIDE, DUAL>;
     constexpr int B = TR::B;
@@ -175,57 +188,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t sa_table = smem_u32(smem + TR::OFF_TABLE);
     const uint32_t sa_tlane = sa_table + lane * 4u;  // this lane's column of the counter table
 
-    // AGENT: CTA 0 of the grid owns no tile.  It walks the descriptor rows in tile order, one thread per bin, and
-    // replaces every AGGREGATE by the exclusive prefix of the tiles before it (flag INCLUSIVE), so a tile learns its
-    // offsets by polling its OWN row: ~2 L2 round trips after its counts were published, where the decoupled
-    // look-back of every tile walks ~20 predecessors in 5-7 dependent round trips (measured: it ends 3 k cycles
-    // after the ranking).  One row per ~35 cycles (AGENT_WIN rows per round trip); the tiles arrive every ~55.
-    if constexpr (AGENT) if (blockIdx.x == 0) {
-        constexpr int AGENT_WIN = 40;
-        constexpr int ANB = (B + THREADS - 1) / THREADS;
-        static_assert(ANB <= 2, "agent: at most two bins per thread");
-        const uint32_t a_not = ((2u * a.parity) & 3u) << 30, a_agg = ((2u * a.parity + 1u) & 3u) << 30;
-        const uint32_t a_inc = ((2u * a.parity + 2u) & 3u) << 30;
-        uint32_t sum[ANB], at[ANB];
-        bool fin[ANB];
-        bool all = true;
-#pragma unroll
-        for (int j = 0; j < ANB; ++j) {
-            sum[j] = 0;
-            at[j] = 0;
-            fin[j] = (tid + j * THREADS >= (uint32_t)B) || a.num_tiles == 0;
-            all = all && fin[j];
-        }
-        while (!all) {
-            all = true;
-#pragma unroll
-            for (int j = 0; j < ANB; ++j) {
-                if (fin[j]) continue;
-                uint32_t *col = a.desc + (tid + j * THREADS);
-                uint32_t v[AGENT_WIN];
-#pragma unroll
-                for (int k = 0; k < AGENT_WIN; ++k)
-                    v[k] = (at[j] + k < a.num_tiles) ? ld_relaxed_gpu(col + (size_t)(at[j] + k) * B) : a_not;
-                bool stop = false;
-                uint32_t adv = 0;
-#pragma unroll
-                for (int k = 0; k < AGENT_WIN; ++k) {
-                    if (!stop && (v[k] & kDescFlagMask) == a_agg) {
-                        st_relaxed_gpu(col + (size_t)(at[j] + k) * B, a_inc | sum[j]);
-                        sum[j] += v[k] & kDescValueMask;
-                        ++adv;
-                    } else {
-                        stop = true;
-                    }
-                }
-                at[j] += adv;
-                fin[j] = at[j] >= a.num_tiles;
-                all = all && fin[j];
-            }
-        }
-        return;
-    }
-    const uint32_t tile = AGENT ? blockIdx.x - 1u : blockIdx.x;
+    const uint32_t tile = blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)TILE;
     const uint32_t n_valid = min((uint32_t)TILE, a.n - tile_base);
     const bool full = (n_valid == (uint32_t)TILE);
@@ -261,7 +224,6 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
                     : WIDE ? s_rowtot[bin] : ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu);
     };
 
-    static_assert(!AGENT || !TR::BULK, "the agent serves the look-back of the non-bulk write-out");
     COL_STAMP(0);
     // ---- 0. tile -> shared memory --------------------------------------------------------------
 #ifdef B200_COL_NOTMA
@@ -394,7 +356,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     const uint32_t st_inc = ((2u * a.parity + 2u) & 3u) << 30;
     for (uint32_t bin = tid; bin < (uint32_t)B; bin += THREADS) {
         const uint32_t count = tile_bytes(bin) >> 2;
-        st_relaxed_gpu(a.desc + (size_t)tile * B + bin, ((tile == 0 && !AGENT) ? st_inc : st_agg) | count);
+        st_relaxed_gpu(a.desc + (size_t)tile * B + bin, (tile == 0 ? st_inc : st_agg) | count);
         if (BULK) {
             // The destination of this tile's run of every bin must be known BEFORE the keys are ranked: the
             // run is laid out in shared memory at the 16-byte phase of its destination, so that its body is
@@ -533,7 +495,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     constexpr int NB = (B + LBT - 1) / LBT;
     // (DUAL: the first warps of both groups, in the order in which their turns end)
     const uint32_t lb_slot = !DUAL ? warp : group_b ? 2u * (warp - WA) + 1u : (warp < (uint32_t)WARPS - WA ? 2u * warp : warp + ((uint32_t)WARPS - WA));
-    if constexpr (LBV4 && !BULK && !AGENT && (B % 4 == 0)) {
+    if constexpr (LBV4 && !BULK && (B % 4 == 0)) {
         // Vector look-back: B / 4 threads, four neighbouring bins each, one 16-byte strong load per tile row (a warp
         // issues one strong load per ~55 cycles, measured: the scalar walk spends most of its round on issuing them).
         // The four bins of a thread consume the rows in order, each at its own position `pos`.
@@ -616,23 +578,8 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         for (int j = 0; j < NB; ++j) {
             excl[j] = 0;
             t[j] = (int32_t)tile - 1;
-            done[j] = (tile == 0 && !AGENT) || (u + j * LBT >= (uint32_t)B);
+            done[j] = (tile == 0) || (u + j * LBT >= (uint32_t)B);
             all_done = all_done && done[j];
-        }
-        if (AGENT) {
-            while (!all_done) {
-                all_done = true;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    if (done[j]) continue;
-                    const uint32_t w = ld_relaxed_gpu(a.desc + (size_t)tile * B + (u + j * LBT));
-                    if ((w & kDescFlagMask) == st_inc) {
-                        excl[j] = w & kDescValueMask;
-                        done[j] = true;
-                    }
-                    all_done = all_done && done[j];
-                }
-            }
         }
 #ifdef B200_COL_DEBUG
         long long dbg_rounds = 0;
@@ -676,7 +623,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             if (bin < (uint32_t)B) {
                 const uint32_t count = tile_bytes(bin) >> 2;
                 const uint32_t bin_start = s_binstart[bin] >> 2;
-                if (tile != 0 && !AGENT) st_relaxed_gpu(a.desc + (size_t)tile * B + bin, st_inc | (excl[j] + count));
+                if (tile != 0) st_relaxed_gpu(a.desc + (size_t)tile * B + bin, st_inc | (excl[j] + count));
                 const uint32_t first = a.bin_base[bin] + excl[j];  // destination index of this tile's first key of the bin
                 if (a.carry_out != nullptr && tile == a.num_tiles - 1u) a.carry_out[bin] = first + count;
                 if (!DST) {

@@ -27,10 +27,9 @@ cudaError_t launch_col_variant(const PassArgs &a, cudaStream_t s) {
     constexpr bool WIDE = (g.mode == 4);
     constexpr bool DUAL = WIDE && g.persist == 2;  // mode 4: persist = number of concurrent ranking chains (1 or 2)
     using TR = ColTraits<W, WARPS, ITEMS, PAIRS, DST, WIDE, DUAL>;
-    constexpr bool AGENT = WIDE && g.lb_batch == 0;  // mode 4, lb_batch 0: a scan agent CTA instead of per-tile look-back
     constexpr bool LBV4 = WIDE && g.lb_batch >= 32;  // mode 4, lb_batch 32 + d: 16-byte look-back loads, d rows in flight
-    constexpr int LBD = AGENT ? 1 : LBV4 ? g.lb_batch - 32 : g.lb_batch;
-    auto kernel = colsweep_pass_kernel<W, WARPS, ITEMS, g.min_ctas, LBD, GROUP, PAIRS, DST, WIDE, DUAL, AGENT, LBV4>;
+    constexpr int LBD = LBV4 ? g.lb_batch - 32 : g.lb_batch;
+    auto kernel = colsweep_pass_kernel<W, WARPS, ITEMS, g.min_ctas, LBD, GROUP, PAIRS, DST, WIDE, DUAL, LBV4>;
     static std::atomic<uint64_t> configured{0};  // one bit per device: the attribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -40,7 +39,7 @@ cudaError_t launch_col_variant(const PassArgs &a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured.fetch_or(1ull << (dev & 63), std::memory_order_release);
     }
-    kernel<<<a.num_tiles + (AGENT ? 1u : 0u), g.threads, TR::SMEM_BYTES, s>>>(a);
+    kernel<<<a.num_tiles, g.threads, TR::SMEM_BYTES, s>>>(a);
     return cudaGetLastError();
 }
 

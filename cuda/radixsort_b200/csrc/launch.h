@@ -99,15 +99,17 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 36, 20, 3, 4, 18, 8, 2},  // 73
     {192, 44, 20, 3, 4, 22, 4, 2},  // 74 six warps (3 + 3) x 44 keys, three CTAs per SM
     {320, 28, 12, 3, 4, 14, 4, 2},  // 75 ten warps x 28 keys, three CTAs per SM
-    // mode 4 with lb_batch = 0: CTA 0 is a scan agent that turns the tiles' aggregates into exclusive prefixes
-    {256, 60, 28, 2, 4, 20, 0, 2},  // 76 = 59 with the agent
-    {320, 44, 20, 2, 4, 22, 0, 2},  // 77 = 56 with the agent
-    {256, 60, 28, 2, 4, 30, 0, 2},  // 78
-    {192, 76, 36, 2, 4, 19, 0, 2},  // 79
-    {288, 52, 28, 2, 4, 26, 0, 0},  // 80 = 50 (one chain) with the agent
-    {352, 44, 20, 2, 4, 22, 0, 0},  // 81 = 54 (one chain) with the agent
-    {256, 36, 20, 3, 4, 18, 0, 2},  // 82 = 72 with the agent
-    {256, 52, 28, 2, 4, 26, 0, 2},  // 83
+    // 76-83: were the scan-agent experiment (CTA 0 turns the tiles' aggregates into exclusive prefixes, the tiles poll
+    // their own row: bit-exact, 0.72 ms per pass -- one warp issues a strong load every ~55 cycles, the agent cannot
+    // keep up with a row every 55 cycles; profiles/r02_experiment_scan_agent.patch).  Now plain 4-deep look-back.
+    {256, 60, 28, 2, 4, 20, 4, 2},  // 76
+    {320, 44, 20, 2, 4, 22, 4, 2},  // 77
+    {256, 60, 28, 2, 4, 30, 4, 2},  // 78
+    {192, 76, 36, 2, 4, 19, 4, 2},  // 79
+    {288, 52, 28, 2, 4, 26, 4, 0},  // 80
+    {352, 44, 20, 2, 4, 22, 4, 0},  // 81
+    {256, 36, 20, 3, 4, 18, 4, 2},  // 82
+    {256, 52, 28, 2, 4, 26, 4, 2},  // 83
     // mode 4 with lb_batch = 32 + d: look-back with 16-byte strong loads (four bins per thread), d rows in flight
     {256, 60, 28, 2, 4, 20, 36, 2}, // 84 = 59, d = 4
     {256, 60, 28, 2, 4, 20, 40, 2}, // 85 d = 8
