@@ -229,10 +229,13 @@ int b200sort_profile_read(float *ms, int *tag, int capacity);
 /* Number of kernels this library has launched since load (the bench's gpu_launches). */
 uint64_t b200sort_launch_count(void);
 
-/* Tuning hooks (bench/test use): "variant" selects the digit-pass kernel geometry,
- * "portion_tiles" caps tiles per launch (0 = default; tests use it to exercise the
- * multi-launch path at small n), "hist_ctas_per_sm".  Returns B200SORT_EINVAL for an
- * unknown name or value. */
+/* Tuning hooks (bench/test use): "variant" selects the digit-pass kernel by its number in
+ * csrc/launch.h (-1 = automatic: the column sweep with two ranking chains for digits of >= 4 bits,
+ * ballot rank below), "portion_tiles" caps tiles per launch (0 = default; tests use it to
+ * exercise the multi-launch path at small n), "hist_ctas_per_sm", "safe_rank" (1 = an
+ * atomic-rank request is served by the column sweep), "prefetch_tiles" (L2 prefetch distance
+ * of the default kernel in tiles; -1 = one per SM, 0 = off), "dst_bulk", "host_overlap",
+ * "scan_variant".  Returns B200SORT_EINVAL for an unknown name or value. */
 int b200sort_set_param(const char *name, int value);
 int b200sort_get_param(const char *name);
 
