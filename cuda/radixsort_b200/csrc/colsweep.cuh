@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     // the scan is the packed scan of two independent column sets, a bin's keys are A's (column order) followed
     // by B's = index order, and each group runs its own chain of turns.  The addend is a per-warp constant, the
     // half of the returned word a per-warp byte selector.
-    static_assert(!DUAL || (WIDE && TR::TILE * 4 < 65536), "DUAL: 16-bit byte positions");
+    static_assert(!DUAL || (WIDE && TR::TILE < 65536), "DUAL: 16-bit positions (in keys)");
     constexpr uint32_t WA = TR::WA;
     const bool group_b = DUAL && warp >= WA;
-    const uint32_t gadd = group_b ? (4u << 16) : 4u;
+    const uint32_t gadd = DUAL ? (group_b ? (1u << 16) : 1u) : 4u;  // DUAL counts keys, the other forms bytes
     const uint32_t gsel = group_b ? 0x4432u : 0x4410u;
     auto tile_bytes = [&](uint32_t bin) -> uint32_t {  // bytes of bin `bin` in this tile (4 per key)
-        return DUAL ? (s_rowtot[bin] & 0xFFFFu) + (s_rowtot[bin] >> 16)
+        return DUAL ? ((s_rowtot[bin] & 0xFFFFu) + (s_rowtot[bin] >> 16)) << 2
                     : WIDE ? s_rowtot[bin] : ((s_rowtot[bin >> 1] >> ((bin & 1u) * 16u)) & 0xFFFFu);
     };
 
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             if (WIDE) {
                 // absolute shared-memory address of the slot (pairs: half of it; the slot is 8 bytes)
                 // DUAL: {B's first position : A's first position} of the bin, B's keys after all of A's
-                if (DUAL) base = s_binstart[row] * 0x10001u + (s_rowtot[row] << 16) + oct[k];
+                if (DUAL) base = (s_binstart[row] >> 2) * 0x10001u + (s_rowtot[row] << 16) + oct[k];
                 else base = s_binstart[row] + oct[k] + (PAIRS ? sa_buf / 2u : sa_buf);
             } else {
                 const uint2 bs = *reinterpret_cast<const uint2 *>(s_binstart + 2 * row);
@@ -470,9 +470,9 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
         for (int g = 0; g < GROUP; ++g)
             if (i0 + g < ITEMS) {
                 if (DUAL) {
-                    const uint32_t pos = __byte_perm(old[g], 0u, gsel);
-                    if (PAIRS) sm_st2(sa_buf + 2u * pos, key[i0 + g], val[i0 + g]);
-                    else sm_st<0>(sa_buf + pos, key[i0 + g]);
+                    const uint32_t pos = __byte_perm(old[g], 0u, gsel);  // in keys
+                    if (PAIRS) sm_st2(sa_buf + 8u * pos, key[i0 + g], val[i0 + g]);
+                    else sm_st<0>(sa_buf + 4u * pos, key[i0 + g]);
                 } else if (WIDE) {
                     if (PAIRS) sm_st2(2u * old[g], key[i0 + g], val[i0 + g]);
                     else sm_st<0>(old[g], key[i0 + g]);

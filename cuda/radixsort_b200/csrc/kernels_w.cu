@@ -240,6 +240,16 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 107: return launch_modes<107>(pairs, dst, a, s);
     case 108: return launch_modes<108>(pairs, dst, a, s);
     case 109: return launch_modes<109>(pairs, dst, a, s);
+    case 110: return launch_modes<110>(pairs, dst, a, s);
+    case 111: return launch_modes<111>(pairs, dst, a, s);
+    case 112: return launch_modes<112>(pairs, dst, a, s);
+    case 113: return launch_modes<113>(pairs, dst, a, s);
+    case 114: return launch_modes<114>(pairs, dst, a, s);
+    case 115: return launch_modes<115>(pairs, dst, a, s);
+    case 116: return launch_modes<116>(pairs, dst, a, s);
+    case 117: return launch_modes<117>(pairs, dst, a, s);
+    case 118: return launch_modes<118>(pairs, dst, a, s);
+    case 119: return launch_modes<119>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

@@ -18,7 +18,7 @@ struct PassVariant {
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA; mode 4: concurrent ranking chains (2 = two warp groups)
 };
-constexpr int kNumVariants = 110;
+constexpr int kNumVariants = 120;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -122,7 +122,7 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {256, 60, 28, 2, 4, 20, 34, 2}, // 92 = 84, d = 2
     {256, 60, 28, 2, 4, 20, 35, 2}, // 93 d = 3
     {256, 60, 28, 2, 4, 20, 38, 2}, // 94 d = 6
-    {256, 60, 36, 2, 4, 10, 36, 2}, // 95 10 atomics in flight; 36 pairs per thread -- the default (kDualVariant)
+    {256, 76, 36, 2, 4, 13, 36, 2}, // 95 THE DEFAULT (kDualVariant): 76 keys / 36 pairs per thread, 13 atomics in flight
     {256, 60, 28, 2, 4, 15, 36, 2}, // 96
     {256, 60, 28, 2, 4, 30, 36, 2}, // 97
     {256, 60, 28, 2, 4, 60, 36, 2}, // 98 a whole turn in flight
@@ -134,9 +134,19 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {320, 44, 20, 2, 4, 22, 36, 2}, // 104 ten warps (5 + 5)
     {384, 36, 20, 2, 4, 18, 36, 2}, // 105 twelve warps (7 + 5)
     {352, 44, 20, 2, 4, 22, 36, 0}, // 106 one chain, eleven warps
-    {256, 60, 28, 2, 4, 12, 36, 2}, // 107
+    {256, 60, 36, 2, 4, 10, 36, 2}, // 107 the default before positions counted keys (60 keys per thread: 16-bit byte positions)
     {256, 60, 36, 2, 4, 10, 36, 2}, // 108 = 95 with 36 pairs per thread
     {256, 60, 36, 2, 4, 10, 34, 2}, // 109
+    {256, 68, 36, 2, 4, 10, 36, 2}, // 110 68 keys per thread (positions count keys, not bytes: tiles of up to 65,535 keys)
+    {256, 76, 36, 2, 4, 10, 36, 2}, // 111
+    {256, 68, 44, 2, 4, 17, 36, 2}, // 112
+    {256, 84, 36, 1, 4, 12, 36, 2}, // 113 one CTA per SM
+    {256, 76, 36, 2, 4, 19, 36, 2}, // 114
+    {256, 76, 36, 2, 4, 13, 36, 2}, // 115
+    {192, 100, 44, 2, 4, 10, 36, 2}, // 116 six warps (3 + 3) x 100 keys
+    {192, 92, 44, 2, 4, 23, 36, 2}, // 117
+    {256, 76, 36, 2, 4, 10, 40, 2}, // 118 8 rows of look-back in flight
+    {256, 76, 36, 2, 4, 10, 35, 2}, // 119 3 rows
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];

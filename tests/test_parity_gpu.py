@@ -332,8 +332,8 @@ def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle, kern
         for kind in ("all_equal", "unique16", "sorted", "iota"):
             kk = oracle.generate(kind, n)
             assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), kind
-        for m in (1, 2, 31, 33, 10367, 10368, 10369, 2 * 10368 + 1,     # around the 10368- and 15360-key tiles
-                  15359, 15360, 15361, 2 * 15360 + 1, 9216, 9217):      # (and the 9216-pair tile)
+        for m in (1, 2, 31, 33, 10367, 10368, 10369, 2 * 10368 + 1,     # around the 10368- and 19456-key tiles
+                  19455, 19456, 19457, 2 * 19456 + 1, 9216, 9217):      # (and the 9216-pair tile)
             kk = oracle.generate("uniform", m)
             assert np.array_equal(dev_sort(rs, kk, 8), oracle.sort_keys(kk, 8)), m
         # unaligned input (no bulk copy): same answer
@@ -357,7 +357,7 @@ def test_unaligned_arrays_with_a_short_prefetch_distance(rs, oracle, offset_word
     arbitrary offsets)."""
     rs.set_param("prefetch_tiles", 1)
     try:
-        n = 5 * 15360 + 777
+        n = 5 * 19456 + 777
         k = oracle.generate("uniform", n)
         v = np.arange(n, dtype=np.uint32)
         pad = np.zeros(offset_words, np.uint32)
