@@ -311,11 +311,12 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
     // Work item it = (row, octet g): 8 columns of one row.  The 4 lanes of a row are neighbours.
     // Row parity swaps the order of the two 16-byte loads so that the 8 lanes of a quarter warp
     // (2 rows x 4 octets) touch 8 different 16-byte bank groups.
-    uint32_t ex[TR::SCAN_ITERS][8];   // exclusive prefix of the item's 8 columns, packed {odd bin : even bin}
-    uint32_t oct[TR::SCAN_ITERS];     // + exclusive prefix of the octets before it in the row
-#pragma unroll
-    for (int k = 0; k < TR::SCAN_ITERS; ++k) {
-        const uint32_t it = tid + k * THREADS;
+    // REREAD (more than 8 warps: 96 registers or fewer per thread): the second half of the scan loads the counters
+    // again instead of keeping 8 prefixes per work item in registers across two barriers.
+    constexpr bool REREAD = WIDE && WARPS > 8;
+    uint32_t ex[REREAD ? 1 : TR::SCAN_ITERS][8];   // exclusive prefix of the item's 8 columns, packed
+    uint32_t oct[REREAD ? 1 : TR::SCAN_ITERS];     // + exclusive prefix of the octets before it in the row
+    auto load_prefix = [&](uint32_t it, uint32_t (&e)[8]) -> uint32_t {  // returns the total of the 8 columns
         const bool active = it < (uint32_t)TR::SCAN_ITEMS;
         const uint32_t row = it >> 2, g = it & 3u, par = row & 1u;
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
@@ -326,25 +327,37 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
             lo = par ? qb : qa;
             hi = par ? qa : qb;
         }
-        uint32_t tot;
-        {
-            ex[k][0] = 0;
-            ex[k][1] = lo.x;
-            ex[k][2] = ex[k][1] + lo.y;
-            ex[k][3] = ex[k][2] + lo.z;
-            ex[k][4] = ex[k][3] + lo.w;
-            ex[k][5] = ex[k][4] + hi.x;
-            ex[k][6] = ex[k][5] + hi.y;
-            ex[k][7] = ex[k][6] + hi.z;
-            tot = ex[k][7] + hi.w;
-        }
+        e[0] = 0;
+        e[1] = lo.x;
+        e[2] = e[1] + lo.y;
+        e[3] = e[2] + lo.z;
+        e[4] = e[3] + lo.w;
+        e[5] = e[4] + hi.x;
+        e[6] = e[5] + hi.y;
+        e[7] = e[6] + hi.z;
+        return e[7] + hi.w;
+    };
+    auto quad_inclusive = [&](uint32_t tot, uint32_t g) -> uint32_t {  // inclusive prefix over the 4 lanes of a row
         uint32_t incl = tot;
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, 1, 4);
         if (g >= 1u) incl += t;
         t = __shfl_up_sync(0xffffffffu, incl, 2, 4);
         if (g >= 2u) incl += t;
-        oct[k] = incl - tot;
-        if (active && g == 3u) s_rowtot[row] = incl;
+        return incl;
+    };
+#pragma unroll
+    for (int k = 0; k < TR::SCAN_ITERS; ++k) {
+        const uint32_t it = tid + k * THREADS;
+        const uint32_t row = it >> 2, g = it & 3u;
+        uint32_t e[8];
+        const uint32_t tot = load_prefix(it, e);
+        const uint32_t incl = quad_inclusive(tot, g);
+        if (!REREAD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ex[k][j] = e[j];
+            oct[k] = incl - tot;
+        }
+        if (it < (uint32_t)TR::SCAN_ITEMS && g == 3u) s_rowtot[row] = incl;
     }
     COL_STAMP(6);
     __syncthreads();
@@ -421,22 +434,31 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) colsweep_pass_kernel(con
 #pragma unroll
     for (int k = 0; k < TR::SCAN_ITERS; ++k) {
         const uint32_t it = tid + k * THREADS;
-        if (it < (uint32_t)TR::SCAN_ITEMS) {
+        if (it < (uint32_t)TR::SCAN_ITEMS) {   // whole warps (SCAN_ITEMS and THREADS are multiples of 32)
             const uint32_t row = it >> 2, g = it & 3u, par = row & 1u;
+            uint32_t e[8], o;
+            if (REREAD) {
+                const uint32_t tot = load_prefix(it, e);
+                o = quad_inclusive(tot, g) - tot;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] = ex[k][j];
+                o = oct[k];
+            }
             uint32_t base;
             if (WIDE) {
                 // absolute shared-memory address of the slot (pairs: half of it; the slot is 8 bytes)
                 // DUAL: {B's first position : A's first position} of the bin, B's keys after all of A's
-                if (DUAL) base = (s_binstart[row] >> 2) * 0x10001u + (s_rowtot[row] << 16) + oct[k];
-                else base = s_binstart[row] + oct[k] + (PAIRS ? sa_buf / 2u : sa_buf);
+                if (DUAL) base = (s_binstart[row] >> 2) * 0x10001u + (s_rowtot[row] << 16) + o;
+                else base = s_binstart[row] + o + (PAIRS ? sa_buf / 2u : sa_buf);
             } else {
                 const uint2 bs = *reinterpret_cast<const uint2 *>(s_binstart + 2 * row);
-                base = (bs.x | (bs.y << 16)) + oct[k];  // byte positions < 2^16: no carry between the halves
+                base = (bs.x | (bs.y << 16)) + o;  // byte positions < 2^16: no carry between the halves
             }
             uint4 lo, hi;
             {
-            lo.x = base + ex[k][0]; lo.y = base + ex[k][1]; lo.z = base + ex[k][2]; lo.w = base + ex[k][3];
-            hi.x = base + ex[k][4]; hi.y = base + ex[k][5]; hi.z = base + ex[k][6]; hi.w = base + ex[k][7];
+            lo.x = base + e[0]; lo.y = base + e[1]; lo.z = base + e[2]; lo.w = base + e[3];
+            hi.x = base + e[4]; hi.y = base + e[5]; hi.z = base + e[6]; hi.w = base + e[7];
             }
             const uint32_t rb = sa_table + row * 128u + g * 32u;
             sm_st4(rb + par * 16u, par ? hi : lo);

@@ -250,6 +250,12 @@ cudaError_t B200_CAT(launch_pass_w, B200_W)(int variant, bool pairs, bool dst, c
     case 117: return launch_modes<117>(pairs, dst, a, s);
     case 118: return launch_modes<118>(pairs, dst, a, s);
     case 119: return launch_modes<119>(pairs, dst, a, s);
+    case 120: return launch_modes<120>(pairs, dst, a, s);
+    case 121: return launch_modes<121>(pairs, dst, a, s);
+    case 122: return launch_modes<122>(pairs, dst, a, s);
+    case 123: return launch_modes<123>(pairs, dst, a, s);
+    case 124: return launch_modes<124>(pairs, dst, a, s);
+    case 125: return launch_modes<125>(pairs, dst, a, s);
 #endif
     default: return cudaErrorInvalidValue;
     }

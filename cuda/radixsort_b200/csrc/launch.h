@@ -18,7 +18,7 @@ struct PassVariant {
     int lb_batch;  // look-back descriptors in flight per bin thread
     int persist;   // 1: persistent CTAs that prefetch their next tile; 2: one tile per CTA, loaded by TMA; mode 4: concurrent ranking chains (2 = two warp groups)
 };
-constexpr int kNumVariants = 120;
+constexpr int kNumVariants = 126;
 constexpr PassVariant kVariants[kNumVariants] = {
     {256, 30, 20, 4, 0, 5, 8, 0},   //  0 default: table(5 bits) + 3 ballots
     {256, 30, 20, 4, 1, 0, 8, 0},   //  1 atomic rank (selected only after the self test passes)
@@ -147,6 +147,12 @@ constexpr PassVariant kVariants[kNumVariants] = {
     {192, 92, 44, 2, 4, 23, 36, 2}, // 117
     {256, 76, 36, 2, 4, 10, 40, 2}, // 118 8 rows of look-back in flight
     {256, 76, 36, 2, 4, 10, 35, 2}, // 119 3 rows
+    {320, 60, 28, 2, 4, 12, 36, 2}, // 120 ten warps (5 + 5: balanced chains) x 60 keys; the scan re-reads the counters
+    {320, 60, 28, 2, 4, 20, 36, 2}, // 121
+    {320, 52, 28, 2, 4, 13, 36, 2}, // 122
+    {384, 44, 20, 2, 4, 11, 36, 2}, // 123 twelve warps (7 + 5) x 44 keys
+    {448, 44, 20, 2, 4, 11, 36, 2}, // 124 fourteen warps (7 + 7) x 44 keys
+    {320, 60, 28, 2, 4, 10, 36, 2}, // 125
 };
 inline int tile_keys(int variant, bool pairs) {
     const PassVariant &g = kVariants[variant];
