@@ -39,6 +39,7 @@ struct Params {
     std::atomic<int> dst_bulk{1};        // digit pass with per-bin destinations, keys only: bulk-copy write-out
     std::atomic<int> host_overlap{1};    // host-pointer path: chunked upload + MSD split + per-bucket download
     std::atomic<int> scan_variant{8};    // tile geometry of b200sort_exclusive_scan (scan.cuh: kScanGeom)
+    std::atomic<int> scan_prefetch_tiles{-1}; // exclusive scan: L2 prefetch distance in tiles (-1 = 8 MiB ahead, 0 = off)
     std::atomic<int> prefetch_tiles{-1}; // column sweep: L2 prefetch distance in tiles; -1 = one tile per SM ahead, 0 = off
 } g_params;
 
@@ -793,6 +794,11 @@ int b200sort_set_param(const char *name, int value) {
         g_params.prefetch_tiles = value;
         return 0;
     }
+    if (!strcmp(name, "scan_prefetch_tiles")) {
+        if (value < -1 || value > (1 << 20)) return B200SORT_EINVAL;
+        g_params.scan_prefetch_tiles = value;
+        return 0;
+    }
     return B200SORT_EINVAL;
 }
 
@@ -807,6 +813,7 @@ int b200sort_get_param(const char *name) {
     if (!strcmp(name, "safe_rank")) return g_params.safe_rank;
     if (!strcmp(name, "scan_variant")) return g_params.scan_variant;
     if (!strcmp(name, "prefetch_tiles")) return g_params.prefetch_tiles;
+    if (!strcmp(name, "scan_prefetch_tiles")) return g_params.scan_prefetch_tiles;
     if (!strcmp(name, "host_overlap")) return g_params.host_overlap;
     if (!strcmp(name, "dst_bulk")) return g_params.dst_bulk;
     if (!strcmp(name, "rank_mode")) return check_device() ? -1 : variant_mode(effective_variant(8));
@@ -1020,16 +1027,18 @@ int b200sort_exclusive_scan(const uint32_t *d_in, uint64_t n, uint32_t *d_out, v
     CU(cudaMemsetAsync(d_temp, 0, (tiles + 1) * sizeof(uint64_t), s));  // descriptors + the ticket of the persistent form
     g_launches.fetch_add(1, std::memory_order_relaxed);
     uint64_t *desc = static_cast<uint64_t *>(d_temp);
+    const int pfp = g_params.scan_prefetch_tiles.load();
+    const uint32_t pf = pfp >= 0 ? (uint32_t)pfp : (uint32_t)((8u << 20) / (tile_elems * 4u));
     switch (sv) {
-    case 0: exclusive_scan_kernel<256, 4><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
-    case 1: exclusive_scan_kernel<512, 4><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc); break;
-    case 2: exclusive_scan_kernel<512, 8><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc); break;
-    case 3: exclusive_scan_kernel<1024, 4><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc); break;
-    case 4: exclusive_scan_kernel<1024, 8><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc); break;
-    case 5: exclusive_scan_kernel<128, 8><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
-    case 6: exclusive_scan_kernel<256, 8><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
-    case 7: exclusive_scan_kernel<256, 16><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc); break;
-    case 8: exclusive_scan_kernel<128, 16><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc); break;
+    case 0: exclusive_scan_kernel<256, 4><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 1: exclusive_scan_kernel<512, 4><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 2: exclusive_scan_kernel<512, 8><<<(unsigned)tiles, 512, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 3: exclusive_scan_kernel<1024, 4><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 4: exclusive_scan_kernel<1024, 8><<<(unsigned)tiles, 1024, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 5: exclusive_scan_kernel<128, 8><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 6: exclusive_scan_kernel<256, 8><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 7: exclusive_scan_kernel<256, 16><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, desc, pf); break;
+    case 8: exclusive_scan_kernel<128, 16><<<(unsigned)tiles, 128, 0, s>>>(d_in, d_out, n, desc, pf); break;
     case 9: CU((launch_scan_persistent<1024, 4>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
     case 10: CU((launch_scan_persistent<512, 8>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;
     case 11: CU((launch_scan_persistent<512, 4>(d_in, d_out, n, desc, (uint32_t)tiles, s))); break;

@@ -35,8 +35,14 @@ __device__ __forceinline__ void st_relaxed_gpu64(uint64_t *p, uint64_t v) {
 // last partial tile is handled with scalar accesses.
 template <int kScanThreads, int kScanVecs>
 __global__ void __launch_bounds__(kScanThreads) exclusive_scan_kernel(const uint32_t *in, uint32_t *out, uint64_t n,
-                                                                       uint64_t *desc) {
+                                                                       uint64_t *desc, uint32_t prefetch) {
     constexpr int kScanTile = kScanThreads * kScanVecs * 4;
+    // a tile `prefetch` tiles further on is requested into L2 (the copy engine does it; 16-byte aligned input only)
+    if (prefetch != 0u && threadIdx.x == 0) {
+        const uint64_t pt = blockIdx.x + (uint64_t)prefetch;
+        if ((pt + 1) * kScanTile <= n && (reinterpret_cast<uintptr_t>(in) & 15u) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in + pt * kScanTile), "r"((uint32_t)kScanTile * 4u) : "memory");
+    }
     __shared__ uint32_t s_warp_tot[32];
     __shared__ uint32_t s_prefix;
     __shared__ uint32_t s_total;

@@ -235,7 +235,8 @@ uint64_t b200sort_launch_count(void);
  * exercise the multi-launch path at small n), "hist_ctas_per_sm", "safe_rank" (1 = an
  * atomic-rank request is served by the column sweep), "prefetch_tiles" (L2 prefetch distance
  * of the default kernel in tiles; -1 = one per SM, 0 = off), "dst_bulk", "host_overlap",
- * "scan_variant".  Returns B200SORT_EINVAL for an unknown name or value. */
+ * "scan_variant", "scan_prefetch_tiles" (the scan's L2 prefetch distance in tiles; -1 = 8 MiB
+ * ahead, 0 = off).  Returns B200SORT_EINVAL for an unknown name or value. */
 int b200sort_set_param(const char *name, int value);
 int b200sort_get_param(const char *name);
 
