@@ -849,7 +849,7 @@ int b200sort_warmup(uint64_t max_n, int pairs) {
     int rc = check_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(g_host.mu);
-    run_selftest();  // decides the rank mode of this device once
+    if (kTuningBuild) run_selftest();  // the atomic-rank kernels (tuning build only) run after this verdict
     const size_t arr = align_up((size_t)std::max<uint64_t>(max_n, 1) * 4, 256);
     rc = ensure_host_ctx((pairs ? 4 : 2) * arr + temp_upper_bound(std::max<uint64_t>(max_n, 1), 8, pairs != 0));
     if (rc) return rc;

@@ -164,10 +164,11 @@ constexpr int kColVariant = 36;  // column-sweep default geometry
 constexpr int kMinTileKeys = 2048;
 
 // true if (width, variant) is instantiated.  The product library carries only the kernels its automatic choice
-// can select -- ballot rank (kBallotVariant) for digits of <= 3 bits, atomic rank (variant 1; 10 and 35 for the
-// 8-bit digit) for wider ones, and the column sweep (kColVariant: spec-safe fallback, keys with per-bin
-// destinations) for every width.  -DB200_TUNING (B200_TUNING=1 python -m cuda.radixsort_b200.build --force) adds
-// every geometry of the table above for tools/sweep.py and the variant tests.
+// can select -- ballot rank (kBallotVariant) for digits of <= 3 bits, the column sweep with two ranking chains
+// (kDualVariant) for wider ones, and the first column sweep (kColVariant: keys with per-bin destinations and bulk-copy
+// write-out, every width).  -DB200_TUNING (B200_TUNING=1 python -m cuda.radixsort_b200.build --force) adds every
+// geometry of the table above -- the atomic-rank kernels of round 1 among them -- for tools/sweep.py and the variant
+// tests.
 constexpr int kBallotVariant = 16;
 constexpr int kBallotSmallVariant = 28;
 #ifdef B200_TUNING
@@ -182,13 +183,11 @@ constexpr bool variant_compiled(int width, int variant) {
     if (kTuningBuild)
         return variant == 0 || variant == 1 || variant == kBallotVariant || variant == kBallotSmallVariant ||
                (width == 8 && variant > 0 && variant < kNumVariants);
-    if (width <= 3) return variant == kBallotVariant;
-    if (width < 8) return variant == 1;
-    return variant == 1 || variant == 10 || variant == 35;
+    return width <= 3 && variant == kBallotVariant;
 }
 inline bool variant_available(int width, int variant) { return variant_compiled(width, variant); }
 // what a request for an unavailable variant falls back to
-inline int fallback_variant(int width) { return width <= 3 ? kBallotVariant : 1; }
+inline int fallback_variant(int width) { return width <= 3 ? kBallotVariant : kDualVariant; }
 // variants that are instantiated with per-bin destinations (b200sort_digit_pass with d_bin_dst)
 constexpr bool variant_has_dst(int width, int variant) {
     return variant_compiled(width, variant) &&

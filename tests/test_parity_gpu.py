@@ -245,8 +245,8 @@ def test_multi_launch_portions(rs, oracle):
 
 def _variants_in_this_build():
     """Every geometry of csrc/launch.h with the tuning build (B200_TUNING=1), else the kernels the product
-    library carries for the 8-bit digit: atomic rank (1, 10; 35 for pairs), the column sweep (36) and the default,
-    the column sweep with two ranking chains (95)."""
+    library carries for the 8-bit digit: the column sweep (36) and the default, the column sweep with two ranking
+    chains (95)."""
     if os.environ.get("B200_TUNING"):
         try:
             import ctypes
@@ -256,7 +256,7 @@ def _variants_in_this_build():
                 return list(range(lib.b200sort_get_param(b"num_variants")))
         except (OSError, RuntimeError):
             pass
-    return [1, 10, 35, 36, 95]
+    return [36, 95]
 
 
 @pytest.mark.parametrize("variant", _variants_in_this_build())
@@ -290,7 +290,10 @@ def test_atomic_rank_selftest_and_stability(rs, oracle):
     assert verdict in (0, 1)
     rs.set_param("variant", 1)
     try:
-        assert rs.get_param("effective_variant") == (1 if verdict == 1 else 36)   # else: the spec-safe column sweep
+        if rs.get_param("tuning_build"):
+            assert rs.get_param("effective_variant") == (1 if verdict == 1 else 36)   # else: the spec-safe column sweep
+        else:   # the product library does not carry the atomic-rank kernels: the request gets the default kernel
+            assert rs.get_param("effective_variant") == 95
         assert rs.get_param("atomic_rank_ok") == verdict
         for kind in ("unique16", "all_equal", "zipf"):
             n = 300007
@@ -312,7 +315,9 @@ def test_safe_rank_mode_every_width_keys_pairs_and_destinations(rs, oracle, kern
     (the column sweep with two chains, variant 95, digits of >= 4 bits) is such a kernel itself and stays."""
     rs.set_param("safe_rank", 1)
     if kernel == "colsweep":
-        rs.set_param("variant", 1)      # an atomic-rank request: replaced by the column sweep, variant 36
+        # tuning build: an atomic-rank request, which safe_rank replaces by the column sweep (variant 36);
+        # product build (no atomic-rank kernels): that kernel by its number
+        rs.set_param("variant", 1 if rs.get_param("tuning_build") else 36)
     try:
         assert rs.get_param("safe_rank") == 1
         if kernel == "colsweep":
