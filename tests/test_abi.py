@@ -90,6 +90,13 @@ def test_argument_errors_without_touching_the_gpu(rs):
     assert lib.b200sort_mgpu_shutdown() == 0
     assert lib.b200sort_set_param(b"variant", 9999) == -1
     assert lib.b200sort_set_param(b"variant", -1) == 0     # automatic choice
+    # L2 prefetch distances of the digit pass and of the scan: -1 = automatic, 0 = off
+    for name in (b"prefetch_tiles", b"scan_prefetch_tiles"):
+        assert lib.b200sort_get_param(name) == -1
+        assert lib.b200sort_set_param(name, 0) == 0 and lib.b200sort_get_param(name) == 0
+        assert lib.b200sort_set_param(name, 64) == 0 and lib.b200sort_get_param(name) == 64
+        assert lib.b200sort_set_param(name, -2) == -1
+        assert lib.b200sort_set_param(name, -1) == 0
     assert lib.b200sort_set_param(b"no_such_param", 1) == -1
     assert b"invalid" in lib.b200sort_error_string(-1)
     assert lib.b200sort_version() == 100
