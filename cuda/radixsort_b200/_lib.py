@@ -50,6 +50,10 @@ SIGNATURES = {
                                 C.c_void_p]),
     "b200sort_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "b200sort_keys_low_bits": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "b200sort_pairs_low_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "b200sort_histogram": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),
     "b200sort_digit_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,

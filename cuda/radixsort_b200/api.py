@@ -222,8 +222,9 @@ def _workspace(device) -> Workspace:
     return _default_ws[key]
 
 
-def sort_keys(keys, nbits: int = 8, out=None, workspace: Workspace | None = None, stream=None):
-    """Device-resident sort: b200sort_keys.  Asynchronous on the current (or given) stream."""
+def sort_keys(keys, nbits: int = 8, out=None, workspace: Workspace | None = None, stream=None, key_bits: int = 32):
+    """Device-resident sort: b200sort_keys.  Asynchronous on the current (or given) stream.
+    key_bits < 32: the caller knows that all keys agree in their bits >= key_bits (b200sort_keys_low_bits)."""
     torch = _torch()
     kp = _dev_ptr(keys, "keys")
     n = keys.numel()
@@ -234,13 +235,17 @@ def sort_keys(keys, nbits: int = 8, out=None, workspace: Workspace | None = None
     need = temp_bytes(n, nbits, False)
     tmp = ws.get(need)
     lib = _lib.load()
-    _lib.check(lib.b200sort_keys(kp, n, op, tmp.data_ptr(), tmp.numel(), nbits, _stream_ptr(stream)))
+    if key_bits == 32:
+        _lib.check(lib.b200sort_keys(kp, n, op, tmp.data_ptr(), tmp.numel(), nbits, _stream_ptr(stream)))
+    else:
+        _lib.check(lib.b200sort_keys_low_bits(kp, n, op, tmp.data_ptr(), tmp.numel(), nbits, key_bits,
+                                              _stream_ptr(stream)))
     return out
 
 
 def sort_pairs(keys, vals, nbits: int = 8, out_keys=None, out_vals=None,
-               workspace: Workspace | None = None, stream=None):
-    """Device-resident stable key/value sort: b200sort_pairs."""
+               workspace: Workspace | None = None, stream=None, key_bits: int = 32):
+    """Device-resident stable key/value sort: b200sort_pairs (key_bits < 32: b200sort_pairs_low_bits)."""
     torch = _torch()
     kp, vp = _dev_ptr(keys, "keys"), _dev_ptr(vals, "vals")
     n = keys.numel()
@@ -251,8 +256,12 @@ def sort_pairs(keys, vals, nbits: int = 8, out_keys=None, out_vals=None,
     ws = workspace or _workspace(keys.device)
     tmp = ws.get(temp_bytes(n, nbits, True))
     lib = _lib.load()
-    _lib.check(lib.b200sort_pairs(kp, vp, n, _dev_ptr(out_keys, "out_keys"), _dev_ptr(out_vals, "out_vals"),
-                                  tmp.data_ptr(), tmp.numel(), nbits, _stream_ptr(stream)))
+    if key_bits == 32:
+        _lib.check(lib.b200sort_pairs(kp, vp, n, _dev_ptr(out_keys, "out_keys"), _dev_ptr(out_vals, "out_vals"),
+                                      tmp.data_ptr(), tmp.numel(), nbits, _stream_ptr(stream)))
+    else:
+        _lib.check(lib.b200sort_pairs_low_bits(kp, vp, n, _dev_ptr(out_keys, "out_keys"), _dev_ptr(out_vals, "out_vals"),
+                                               tmp.data_ptr(), tmp.numel(), nbits, key_bits, _stream_ptr(stream)))
     return out_keys, out_vals
 
 

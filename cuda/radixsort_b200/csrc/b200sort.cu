@@ -334,7 +334,9 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
     h.zero_ptr = reinterpret_cast<uint4 *>(desc);
     h.zero_vecs = L.desc_bytes / 16;
     h.passes = pl;
-    CU(launch_hist(pl.width, nbits <= kMaxRadixBits && key_bits == 32, h, hist_grid(n, pl.count, pl.width), stream));
+    // the compile-time form of K1 covers ceil(32 / nBits) digits at shifts p * nBits, the last one of any width
+    const bool k1_fixed = nbits <= kMaxRadixBits && pl.count == (32 + nbits - 1) / nbits;
+    CU(launch_hist(pl.width, k1_fixed, h, hist_grid(n, pl.count, pl.width), stream));
     CU(profile_mark(stream, 0));
 
     const uint64_t portion_keys = L.portion_tiles * (uint64_t)tile;
@@ -363,7 +365,11 @@ int run_sort(const uint32_t *kin, const uint32_t *vin, uint64_t n, uint32_t *kou
             a.mask = (1u << pl.bits[p]) - 1u;
             a.parity = (uint32_t)(p & 1);
             a.prefetch = prefetch_distance();
-            CU(launch_pass(pl.width, variant, pairs, false, a, stream));
+            // A digit narrower than the others (the last one when nBits does not divide the key width) runs the kernel
+            // of its own width: a smaller counter table.  Bases, carries and descriptors are indexed by bin and keep
+            // the stride of the widest digit, which they fit.
+            const int w = pl.width >= 4 ? std::max<int>(pl.bits[p], 4) : pl.width;
+            CU(launch_pass(w, variant, pairs, false, a, stream));
         }
         CU(profile_mark(stream, p + 1));
     }
@@ -833,6 +839,21 @@ int b200sort_pairs(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_
     if (n > 0 && (!d_vals_in || !d_vals_out)) return fail(B200SORT_EINVAL, "null value buffer");
     return run_sort(d_keys_in, d_vals_in, n, d_keys_out, d_vals_out, d_temp, temp_bytes, nBits,
                     (cudaStream_t)stream);
+}
+
+int b200sort_keys_low_bits(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp, size_t temp_bytes,
+                           int nBits, int key_bits, void *stream) {
+    if (key_bits < 1 || key_bits > 32) return fail(B200SORT_EINVAL, "key_bits must be in 1..32");
+    return run_sort(d_in, nullptr, n, d_out, nullptr, d_temp, temp_bytes, nBits, (cudaStream_t)stream, key_bits);
+}
+
+int b200sort_pairs_low_bits(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                            uint32_t *d_keys_out, uint32_t *d_vals_out, void *d_temp, size_t temp_bytes,
+                            int nBits, int key_bits, void *stream) {
+    if (key_bits < 1 || key_bits > 32) return fail(B200SORT_EINVAL, "key_bits must be in 1..32");
+    if (n > 0 && (!d_vals_in || !d_vals_out)) return fail(B200SORT_EINVAL, "null value buffer");
+    return run_sort(d_keys_in, d_vals_in, n, d_keys_out, d_vals_out, d_temp, temp_bytes, nBits,
+                    (cudaStream_t)stream, key_bits);
 }
 
 int b200sort_keys_host(const uint32_t *h_in, uint64_t n, uint32_t *h_out, int nBits, int blockSize) {

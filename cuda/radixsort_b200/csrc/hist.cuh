@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a)
     }
 
     uint32_t *col = s_hist + lane;  // this lane's column
+    // P_CT > 0: digits of W bits at shifts 0, W, 2W, ...; the last one may be narrower (32 % W != 0, or keys that
+    // are known to agree above some bit: b200sort_keys_low_bits)
+    const uint32_t last_mask = P_CT > 0 ? (1u << a.passes.bits[P_CT > 0 ? P_CT - 1 : 0]) - 1u : 0u;
     auto tally = [&](uint32_t key) {
         if constexpr (P_CT < 0) {
             atomicAdd(col + (((key >> shift0) & mask0) << 5), 1u);
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const HistArgs a)
 #pragma unroll
             for (int p = 0; p < (P_CT > 0 ? P_CT : kMaxPasses); ++p) {
                 if (P_CT == 0 && p >= P) break;
-                const uint32_t d = P_CT > 0 ? ((key >> (p * W)) & (B - 1))
+                const uint32_t d = P_CT > 0 ? ((key >> (p * W)) & (p == P_CT - 1 ? last_mask : (uint32_t)(B - 1)))
                                             : ((key >> a.passes.shift[p]) & ((1u << a.passes.bits[p]) - 1u));
                 atomicAdd(col + ((p * B + d) << 5), 1u);
             }

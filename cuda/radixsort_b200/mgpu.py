@@ -61,6 +61,17 @@ def choose_owner(global_hist: np.ndarray, world: int) -> np.ndarray:
     return owner
 
 
+def shard_key_bits(owner: np.ndarray, rank: int, shift: int) -> int:
+    """Bits of a key that can still differ inside rank's shard after a range partition on the TOP_BITS-wide window
+    at `shift` (all keys agree above the window, or the window would sit higher): the bins a rank owns are a range
+    [lo, hi] of window values, which agree in their leading bits above the highest bit of lo ^ hi."""
+    mine = np.nonzero(np.asarray(owner) == rank)[0]
+    if mine.size == 0:
+        return 32
+    lo, hi = int(mine[0]), int(mine[-1])
+    return min(32, shift + int(lo ^ hi).bit_length()) if lo != hi else max(1, shift)
+
+
 def plan_exchange(counts_all: np.ndarray, rank: int, owner=None):
     """counts_all[src][bin] -> everything a rank needs for the exchange.
 
@@ -193,10 +204,11 @@ class DeviceOps:
         return self.api.digit_pass(keys, shift, bits, vals=vals, out_keys=out, out_vals=out_vals,
                                    bin_dst=bin_dst, workspace=self.ws)
 
-    def sort(self, keys, nbits, out, vals=None, out_vals=None):
+    def sort(self, keys, nbits, out, vals=None, out_vals=None, key_bits=32):
         if vals is None:
-            return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws)
-        return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws)
+            return self.api.sort_keys(keys, nbits, out=out, workspace=self.ws, key_bits=key_bits)
+        return self.api.sort_pairs(keys, vals, nbits, out_keys=out, out_vals=out_vals, workspace=self.ws,
+                                   key_bits=key_bits)
 
     def route(self, keys, values, ties):
         return self.api.route(keys, values, ties, with_counts=True)
@@ -408,7 +420,7 @@ class ShardedSorter:
             if vals is not None:
                 self._all_to_all(self.recv_v[:my_total], part_v, plan["recv_counts"], plan["send_counts"])
             t.mark("exchange")
-        return self._local_sort(my_total, vals is not None)
+        return self._local_sort(my_total, vals is not None, key_bits=shard_key_bits(plan["owner"], rank, shift))
 
     def _ensure_capacity(self, plan, n_local, vals):
         need = int(plan["totals"].max())
@@ -421,17 +433,25 @@ class ShardedSorter:
         if vals is not None:
             self._allocate_values()
 
-    def _local_sort(self, my_total, pairs):
+    def _local_sort(self, my_total, pairs, key_bits=32):
+        """key_bits < 32: the shard's keys agree in their bits >= key_bits (the splitters fixed them), so the local
+        sort skips those digits (b200sort_keys_low_bits)."""
         ops, t = self.ops, self.timer
         out = self.out[:my_total]
+        # worth it only while the number of digit passes stays the same (the narrower top digit runs a smaller
+        # kernel): with fewer passes the histogram kernel leaves its compile-time form and costs more than a pass
+        if -(-key_bits // self.nbits) != -(-32 // self.nbits):
+            key_bits = 32
+        kw = {"key_bits": key_bits} if key_bits < 32 else {}
+        self.last_key_bits = key_bits
         if not pairs:
             if my_total:
-                ops.sort(self.recv[:my_total], self.nbits, out)
+                ops.sort(self.recv[:my_total], self.nbits, out, **kw)
             t.mark("local_sort")
             return out
         out_v = self.out_v[:my_total]
         if my_total:
-            ops.sort(self.recv[:my_total], self.nbits, out, vals=self.recv_v[:my_total], out_vals=out_v)
+            ops.sort(self.recv[:my_total], self.nbits, out, vals=self.recv_v[:my_total], out_vals=out_v, **kw)
         t.mark("local_sort")
         return out, out_v
 

@@ -147,6 +147,18 @@ int b200sort_pairs(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_
                    uint32_t *d_keys_out, uint32_t *d_vals_out, void *d_temp,
                    size_t temp_bytes, int nBits, void *stream);
 
+/* The same sorts for keys that are known to agree in all bits >= key_bits (1..32): only the digits
+ * below key_bits are sorted -- the bucket of an MSD partition, a shard of the multi-GPU sort whose
+ * splitters fixed the top bits.  The result is the full sort if the promise holds, otherwise the keys
+ * are ordered by their low key_bits bits only (stable).  No counterpart in the reference, whose loop
+ * always covers all 32 bits (SourceCode/Parallel7.cu:561); temp storage as for the full sort. */
+int b200sort_keys_low_bits(const uint32_t *d_in, uint64_t n, uint32_t *d_out, void *d_temp,
+                           size_t temp_bytes, int nBits, int key_bits, void *stream);
+
+int b200sort_pairs_low_bits(const uint32_t *d_keys_in, const uint32_t *d_vals_in, uint64_t n,
+                            uint32_t *d_keys_out, uint32_t *d_vals_out, void *d_temp,
+                            size_t temp_bytes, int nBits, int key_bits, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Building blocks, exported for the multi-GPU driver (histogram -> splitters -> partition ->
  * exchange -> local sort) and as the public form of the reference's stage wrappers.

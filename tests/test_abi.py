@@ -83,6 +83,9 @@ def test_argument_errors_without_touching_the_gpu(rs):
     assert lib.b200sort_keys_host(None, 16, o.ctypes.data, 8, 512) == -1
     assert lib.b200sort_keys_host(a.ctypes.data, 0, o.ctypes.data, 8, 512) == 0        # n == 0 no-op
     assert lib.b200sort_keys(None, 0, None, None, 0, 8, None) == 0
+    assert lib.b200sort_keys_low_bits(None, 0, None, None, 0, 8, 29, None) == 0
+    assert lib.b200sort_keys_low_bits(None, 0, None, None, 0, 8, 0, None) == -1       # key_bits
+    assert lib.b200sort_pairs_low_bits(None, None, 0, None, None, None, 0, 8, 33, None) == -1
     # multi-GPU host entry points validate before they look for devices
     assert lib.b200sort_mgpu_keys_host(a.ctypes.data, 16, o.ctypes.data, 0, 512, None, 2) == -1
     assert lib.b200sort_mgpu_keys_host(a.ctypes.data, 16, o.ctypes.data, 8, 0, None, 2) == -1

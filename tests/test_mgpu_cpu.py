@@ -122,8 +122,11 @@ class NumpyOps:
         out_vals.numpy()[:] = vals.numpy()[idx]
         return out, out_vals
 
-    def sort(self, keys, nbits, out, vals=None, out_vals=None):
+    def sort(self, keys, nbits, out, vals=None, out_vals=None, key_bits=32):
         import oracle as O
+        k32 = keys.numpy().view(np.uint32)
+        if key_bits < 32 and k32.size:      # the promise behind b200sort_keys_low_bits: the bits above agree
+            assert np.all((k32 >> np.uint32(key_bits)) == (k32[0] >> np.uint32(key_bits))), key_bits
         if vals is None:
             out.numpy().view(np.uint32)[:] = O.sort_keys(keys.numpy().view(np.uint32), nbits)
             return out

@@ -377,6 +377,25 @@ def test_unaligned_arrays_with_a_short_prefetch_distance(rs, oracle, offset_word
         rs.set_param("prefetch_tiles", -1)
 
 
+@pytest.mark.parametrize("key_bits", [32, 31, 29, 28, 24, 21, 16, 9, 8, 3, 1])
+def test_low_bits_sorts_are_full_sorts_when_the_high_bits_agree(rs, oracle, key_bits):
+    """b200sort_keys_low_bits / _pairs_low_bits: keys that share their bits >= key_bits (a bucket of an MSD
+    partition, a shard of the multi-GPU sort) -- the digits above are skipped, a narrower last digit runs the kernel
+    of its own width, and the result is the oracle's full sort."""
+    n = 3 * 19456 + 1234
+    rng = np.random.default_rng(key_bits)
+    low = rng.integers(0, 1 << key_bits, size=n, dtype=np.uint64).astype(np.uint32)
+    prefix = np.uint32((0xA5C3F00F >> key_bits) << key_bits) if key_bits < 32 else np.uint32(0)
+    k = low | prefix
+    v = np.arange(n, dtype=np.uint32)
+    for nbits in (8, 5, 11):
+        out = rs.sort_keys(to_dev(k), nbits, key_bits=key_bits)
+        assert np.array_equal(to_host(out), oracle.sort_keys(k, nbits)), (key_bits, nbits)
+    ko, vo = rs.sort_pairs(to_dev(k), to_dev(v), 8, key_bits=key_bits)
+    rk, rv = oracle.sort_pairs(k, v, 8)
+    assert np.array_equal(to_host(ko), rk) and np.array_equal(to_host(vo), rv)
+
+
 def test_histogram_matches_tile_table_column_sums(rs, oracle):
     k = oracle.generate("zipf", 300007)
     for shift, bits in ((0, 8), (24, 8), (13, 5), (30, 2), (28, 8)):
