@@ -57,6 +57,26 @@ def test_plan_exchange_is_consistent_across_ranks():
         assert [x[2] for x in spans if x[1]] == sorted(x[2] for x in spans if x[1])   # grouped by source rank
 
 
+def test_shard_key_bits_is_the_common_prefix_of_the_owned_bin_range():
+    """mgpu.shard_key_bits: the local sort of a shard may skip the bits on which all its keys agree.  Checked against
+    a brute-force common prefix of every key value the shard can hold."""
+    rng = np.random.default_rng(7)
+    for world in (1, 2, 3, 5, 8):
+        for _ in range(20):
+            cuts = np.sort(rng.choice(np.arange(1, 256), size=world - 1, replace=False)) if world > 1 else np.array([], int)
+            owner = np.searchsorted(cuts, np.arange(256), side="right")
+            for shift in (24, 16, 0):
+                for r in range(world):
+                    kb = mgpu.shard_key_bits(owner, r, shift)
+                    mine = np.nonzero(owner == r)[0]
+                    lo, hi = int(mine[0]) << shift, ((int(mine[-1]) + 1) << shift) - 1      # key range of the shard
+                    assert 1 <= kb <= 32
+                    assert (lo >> kb) == (hi >> kb) or kb == 32                               # the promise holds ...
+                    if kb > max(1, shift):
+                        assert (lo >> (kb - 1)) != (hi >> (kb - 1))                           # ... and is tight
+    assert mgpu.shard_key_bits(np.zeros(256, int), 3, 24) == 32                               # a rank that owns nothing
+
+
 def test_plan_exchange_offsets_match_a_sequential_walk():
     """bin_recv_offset (vectorised per owner) == the obvious walk over the bins in order, for random count
     matrices and for owners that leave some ranks without bins."""
